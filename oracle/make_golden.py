@@ -90,9 +90,53 @@ def _qr_case(name, nnuc, nframes, ntraj, seed, analyte="127I", symbol="I", with_
     print("golden:", name)
 
 
+def _leaf_vectors():
+    """Outputs of the reference's leaf numerics (numba pdist_ortho, wiener_khinchin, Y2m
+    ufuncs, SR_func1 is covered by the SR cases) on seeded inputs -> leaf_vectors.npz."""
+    import numpy as np
+    refshim.import_reference()
+    import distances, qrax, ddrax  # the reference's modules
+    rng = np.random.default_rng(5)
+    out = {}
+    for k, (n, L, dmax) in enumerate([(9, 4.0, 2.4), (60, 7.3, 3.1), (60, 7.3, 7.0), (33, 12.5, 40.0)]):
+        x, y, z = rng.uniform(0, L, (3, n))
+        x[1], y[1], z[1] = np.mod(x[0] + L / 2, L), y[0], z[0]      # exact half-box tie along x
+        x[2], y[2], z[2] = x[0], np.mod(y[0] + L / 2, L), np.mod(z[0] + L / 2, L)
+        x[3] = L                                                    # np.mod can return L itself
+        idx = np.arange(n) + 1000 * k
+        res = distances.pdist_ortho(x, y, z, L, L * 1.0, L * 1.0, idx, dmax)
+        out["pd%d_in" % k] = np.stack([x, y, z]); out["pd%d_par" % k] = np.array([L, dmax])
+        out["pd%d_idx" % k] = idx
+        for c, nm in enumerate(("dx", "dy", "dz", "dr", "a0", "a1", "prj")):
+            out["pd%d_%s" % (k, nm)] = res[c]
+    z = rng.normal(size=50) + 1j * rng.normal(size=50)
+    out["wk_in"] = z; out["wk_out"] = qrax.wiener_khinchin(z)
+    zn = z.copy(); zn[[3, 4, 20, 48, 49]] = np.nan
+    out["wk_nan_in"] = zn; out["wk_nan_out"] = qrax.wiener_khinchin(zn)
+    r = rng.normal(size=31)
+    out["wk_real_in"] = r; out["wk_real_out"] = ddrax.wiener_khinchin(r)
+    d = rng.normal(size=(3, 40)) * 4
+    dr = np.sqrt((d ** 2).sum(0))
+    class _T(dict):
+        __getitem__ = dict.__getitem__
+    import pandas as pd
+    df = pd.DataFrame({"dx": d[0], "dy": d[1], "dz": d[2], "dr": dr, "time": np.arange(40.0),
+                       "label0": 0, "label1": 1})
+    F = ddrax.cart_to_dipolar_from_df(df)
+    out["dd_in"] = np.vstack([d, dr])
+    for nm in ("$r^{-3}$", "$Y_{2,0}$", "$Y_{2,1}$", "$Y_{2,2}$", "$F_{2,0}$", "$F_{2,1}$", "$F_{2,2}$"):
+        out["dd_" + nm.strip("$").replace("{", "").replace("}", "").replace("^", "").replace(",", "").replace("_", "")] = \
+            np.asarray(F[nm].values)
+    np.savez_compressed(os.path.join(GOLD, "leaf_vectors.npz"), **out)
+    print("golden: leaf_vectors.npz", sorted(out)[:6], "...")
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
+    if "--leaf-only" in sys.argv:
+        return _leaf_vectors()
+    _leaf_vectors()
     # the reference's own (only) known-answer set
     ref_nb = os.path.join(refshim.REFERENCE, "notebooks")
     dst = os.path.join(GOLD, "reference_iodide")
