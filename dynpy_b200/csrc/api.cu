@@ -1,0 +1,469 @@
+// dynpy_b200 — the C-ABI (include/dynpy_b200.h): argument checks, workspace carving,
+// batch loops.  All compute is in the kernels of fft_engine.cuh / kernels_misc.cu.
+#include <stdarg.h>
+
+#include "../../include/dynpy_b200.h"
+#include "kernels.h"
+
+namespace dynpy {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail_cuda(cudaError_t e, const char* where) {
+    set_error("%s: %s", where, cudaGetErrorString(e));
+    cudaGetLastError();  // clear the sticky-less error
+    return DYNPY_ERR_LAUNCH;
+}
+
+static DeviceState g_dev[64];
+
+int get_device_state(DeviceState** out, cudaStream_t st) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64) {
+        set_error("no CUDA device (%s)", e == cudaSuccess ? "bad ordinal" : cudaGetErrorString(e));
+        return DYNPY_ERR_NO_DEVICE;
+    }
+    DeviceState& d = g_dev[dev];
+    if (!d.ready) {
+        cudaDeviceProp prop;
+        DYNPY_CHECK(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+        if (prop.major < 10) {
+            set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+            return DYNPY_ERR_NO_DEVICE;
+        }
+        d.n_sm = prop.multiProcessorCount;
+        DYNPY_CHECK(cudaMalloc(&d.tw4096, 4096 * sizeof(double2)), "cudaMalloc(twiddles)");
+        DYNPY_CHECK(launch_init_twiddles(d.tw4096, st), "init twiddles");
+        DYNPY_CHECK(cudaStreamSynchronize(st), "init twiddles sync");
+        d.ready = true;
+    }
+    *out = &d;
+    return DYNPY_OK;
+}
+
+static inline i64 align_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
+static inline bool pow2(i64 m) { return m > 0 && (m & (m - 1)) == 0; }
+
+static int check_M(i64 M, i64 n) {
+    if (!pow2(M) || M < 32 || M > ((i64)1 << 24)) {
+        set_error("transform length M=%lld must be a power of two in [32, 2^24]", (long long)M);
+        return DYNPY_ERR_INVALID;
+    }
+    if (n < 1 || 2 * n - 1 > M) {
+        set_error("series length n=%lld needs M >= 2n-1 (M=%lld)", (long long)n, (long long)M);
+        return DYNPY_ERR_INVALID;
+    }
+    return DYNPY_OK;
+}
+
+}  // namespace dynpy
+
+using namespace dynpy;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int dynpy_version(void) { return 100; }
+const char* dynpy_last_error(void) { return g_err; }
+
+int dynpy_device_sm_count(void) {
+    DeviceState* d;
+    int rc = get_device_state(&d, 0);
+    return rc ? rc : d->n_sm;
+}
+
+int64_t dynpy_fft_length(int64_t n) {
+    int64_t m = 32;
+    while (m < 2 * n) m <<= 1;
+    return m;
+}
+
+int64_t dynpy_fft_workspace_bytes(int64_t M, int64_t n_fft) {
+    if (M <= DYNPY_ROW_LEN) return 0;
+    if (n_fft < 1) n_fft = 1;
+    return n_fft * M * (int64_t)sizeof(cd);
+}
+
+// ------------------------------------------------------------------------------------------ WK
+int dynpy_wk_acf_sum_f64(const double* re, const double* im, int64_t n_series, int64_t n, int64_t series_stride,
+                         int pack_real_pairs, const double* scale, double* spectrum, int64_t M, void* ws,
+                         int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_M(M, n);
+    if (rc) return rc;
+    if (n_series < 0 || !re || !spectrum || series_stride < n || (pack_real_pairs && im)) {
+        set_error("dynpy_wk_acf_sum_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (pack_real_pairs && scale) {
+        set_error("dynpy_wk_acf_sum_f64: per-series scale is not supported together with pack_real_pairs");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n_series == 0) return DYNPY_OK;
+    DeviceState* d;
+    rc = get_device_state(&d, st);
+    if (rc) return rc;
+    PlanarLoader ld;
+    memset(&ld, 0, sizeof(ld));
+    ld.re = re;
+    ld.nslots = 1;
+    ld.N = n;
+    ld.scale = scale;
+    ld.bias_slot = -1;
+    i64 n_fft;
+    if (pack_real_pairs) {
+        ld.im = re + series_stride;
+        ld.hi = 2 * series_stride;
+        n_fft = (n_series + 1) / 2;
+        ld.n_im_valid = n_series / 2;
+    } else {
+        ld.im = im;
+        ld.hi = series_stride;
+        n_fft = n_series;
+        ld.n_im_valid = n_series;
+    }
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = spectrum;
+    ep.M = M;
+    ep.nslots = 1;
+    ep.acc_pack = 0;
+    i64 T_cap = M > DYNPY_ROW_LEN ? ws_bytes / (M * (i64)sizeof(cd)) : 0;
+    if (M > DYNPY_ROW_LEN && (T_cap < 1 || !ws)) {
+        set_error("workspace too small: need >= %lld bytes", (long long)(M * (i64)sizeof(cd)));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    DYNPY_CHECK(forward_planar_acc(ld, ep, n_fft, M, 1, (cd*)ws, T_cap, d->tw4096, d->n_sm, st), "wk forward");
+    return DYNPY_OK;
+}
+
+int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf, int64_t n_out, double scale,
+                       void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!pow2(M) || M < 32 || M > ((i64)1 << 24) || n_acc < 1 || n_out < 1 || n_out > M || !spectrum || !acf) {
+        set_error("dynpy_ifft_acf_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    SpectrumLoader ld;
+    ld.S = spectrum;
+    ld.M = M;
+    ld.M1 = M > DYNPY_ROW_LEN ? (int)(M / DYNPY_ROW_LEN) : 1;
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = acf;
+    ep.M = M;
+    ep.nslots = 1;
+    ep.n_out = n_out;
+    ep.scale = scale;
+    i64 T_cap = M > DYNPY_ROW_LEN ? ws_bytes / (M * (i64)sizeof(cd)) : 0;
+    if (M > DYNPY_ROW_LEN && (T_cap < 1 || !ws)) {
+        set_error("workspace too small: need >= %lld bytes", (long long)(M * (i64)sizeof(cd)));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    DYNPY_CHECK(forward_spectrum_real(ld, ep, n_acc, M, 1, (cd*)ws, T_cap, d->tw4096, d->n_sm, st), "final transform");
+    return DYNPY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ QR
+int dynpy_qr_efg_to_spectrum_f64(const double* efg, int64_t n_nuclei, int64_t n_frames, double* spectrum, int64_t M,
+                                 void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_M(M, n_frames);
+    if (rc) return rc;
+    if (!efg || !spectrum || n_nuclei < 0) {
+        set_error("dynpy_qr_efg_to_spectrum_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n_nuclei == 0) return DYNPY_OK;
+    DeviceState* d;
+    rc = get_device_state(&d, st);
+    if (rc) return rc;
+    QrLoader ld;
+    ld.V = efg;
+    ld.N = n_frames;
+    ld.nnuc = n_nuclei;
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = spectrum;
+    ep.M = M;
+    ep.nslots = 5;
+    ep.acc_pack = 0x21210ull;  // slots 0..4 -> acc 0,1,2,1,2
+    const i64 n_items = (n_nuclei + 1) / 2;
+    i64 T_cap = M > DYNPY_ROW_LEN ? ws_bytes / (M * (i64)sizeof(cd)) : 0;
+    if (M > DYNPY_ROW_LEN && (T_cap < 5 || !ws)) {
+        set_error("workspace too small: need >= %lld bytes", (long long)(5 * M * (i64)sizeof(cd)));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    DYNPY_CHECK(forward_qr_acc(ld, ep, n_items * 5, M, 5, (cd*)ws, T_cap, d->tw4096, d->n_sm, st), "qr forward");
+    return DYNPY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ DD
+int dynpy_wrap_f64(const double* x, double* out, int64_t n, double L, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !out || n < 0 || !(L > 0.0)) {
+        set_error("dynpy_wrap_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_wrap(x, out, n, L, d->n_sm, st), "wrap");
+    return DYNPY_OK;
+}
+
+int64_t dynpy_pdist_workspace_bytes(int64_t n) {
+    int64_t npairs = n * (n - 1) / 2;
+    return ((npairs + 255) / 256 + 1) * (int64_t)sizeof(int64_t);
+}
+
+int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, int64_t stride, int64_t n, double a,
+                          double b, double c, const int64_t* index, double dmax, double* dx, double* dy, double* dz,
+                          double* dr, int64_t* atom0, int64_t* atom1, int64_t* projection, int64_t* count, void* ws,
+                          int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!count || n < 0 || stride < 1 || (n >= 2 && (!ux || !uy || !uz || !index))) {
+        set_error("dynpy_pdist_ortho_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n >= 2 && (!dx || !dy || !dz || !dr || !atom0 || !atom1 || !projection)) {
+        set_error("dynpy_pdist_ortho_f64: output arrays missing");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n >= 2 && (ws_bytes < dynpy_pdist_workspace_bytes(n) || !ws)) {
+        set_error("dynpy_pdist_ortho_f64: workspace too small (need %lld)", (long long)dynpy_pdist_workspace_bytes(n));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_pdist(ux, uy, uz, stride, n, a, b, c, (const i64*)index, dmax, dx, dy, dz, dr, (i64*)atom0,
+                             (i64*)atom1, (i64*)projection, (i64*)count, (i64*)ws, st), "pdist_ortho");
+    return DYNPY_OK;
+}
+
+int dynpy_dd_pair_count_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                            const int32_t* pair_j, int64_t n_pairs, double a, double b, double c, double rmax,
+                            int64_t* counts, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!coords || !pair_i || !pair_j || !counts || n_frames < 1 || n_pairs < 0 || n_atoms < 1) {
+        set_error("dynpy_dd_pair_count_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    for (i64 p0 = 0; p0 < n_pairs; p0 += (i64)1 << 30) {
+        i64 cnt = n_pairs - p0 < ((i64)1 << 30) ? n_pairs - p0 : ((i64)1 << 30);
+        DYNPY_CHECK(launch_dd_pair_count(coords, n_frames, pair_i + p0, pair_j + p0, cnt, a, b, c, rmax,
+                                         (i64*)counts + p0, st), "dd pair count");
+    }
+    return DYNPY_OK;
+}
+
+static i64 dd_item_bytes(i64 N, i64 M) {
+    i64 z = align_up((i64)DD_NSLOTS * 2 * N * 8, 256);
+    i64 t = M > DYNPY_ROW_LEN ? (i64)DD_NSLOTS * M * (i64)sizeof(cd) : 0;
+    return z + t + 16;
+}
+int64_t dynpy_dd_workspace_bytes(int64_t n_frames, int64_t M, int64_t items) {
+    if (items < 1) items = 1;
+    return items * dd_item_bytes(n_frames, M) + 1024;
+}
+
+int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                                   const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
+                                   double* spectrum, int64_t M, void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_M(M, n_frames);
+    if (rc) return rc;
+    if (!coords || !pair_i || !pair_j || !spectrum || n_pairs < 0 || n_atoms < 1 || !ws) {
+        set_error("dynpy_dd_pairs_to_spectrum_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n_pairs == 0) return DYNPY_OK;
+    DeviceState* d;
+    rc = get_device_state(&d, st);
+    if (rc) return rc;
+    const i64 N = n_frames;
+    i64 cap = (ws_bytes - 1024) / dd_item_bytes(N, M);
+    if (cap < 1) {
+        set_error("dynpy_dd_pairs_to_spectrum_f64: workspace too small (need >= %lld bytes)",
+                  (long long)dynpy_dd_workspace_bytes(N, M, 1));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    const i64 items = (n_pairs + 1) / 2;
+    if (cap > items) cap = items;
+    // carve: bias[2*cap] | Z[cap][11][2][N] | T[cap*11][M]
+    char* base = (char*)ws;
+    double* bias = (double*)base;
+    i64 off = align_up(cap * 16, 256);
+    double* Z = (double*)(base + off);
+    off += align_up(cap * (i64)DD_NSLOTS * 2 * N * 8, 256);
+    cd* T = M > DYNPY_ROW_LEN ? (cd*)(base + off) : nullptr;
+
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = spectrum;
+    ep.M = M;
+    ep.nslots = DD_NSLOTS;
+    const int acc_of_slot[DD_NSLOTS] = {0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6};
+    for (int s = 0; s < DD_NSLOTS; ++s) ep.acc_pack |= (unsigned long long)acc_of_slot[s] << (4 * s);
+
+    for (i64 it0 = 0; it0 < items; it0 += cap) {
+        const i64 cnt = items - it0 < cap ? items - it0 : cap;
+        DYNPY_CHECK(launch_dd_words(coords, n_atoms, N, pair_i, pair_j, 2 * it0, n_pairs, cnt, a, b, c, Z, bias, st),
+                    "dd words");
+        PlanarLoader ld;
+        memset(&ld, 0, sizeof(ld));
+        ld.re = Z;
+        ld.im = Z + N;
+        ld.hi = (i64)DD_NSLOTS * 2 * N;
+        ld.lo = 2 * N;
+        ld.n_im_valid = (i64)1 << 62;
+        ld.nslots = DD_NSLOTS;
+        ld.N = N;
+        ld.bias = bias;
+        ld.bias_slot = 5;
+        DYNPY_CHECK(forward_planar_acc(ld, ep, cnt * DD_NSLOTS, M, DD_NSLOTS, T, cnt * DD_NSLOTS, d->tw4096, d->n_sm, st),
+                    "dd forward");
+    }
+    return DYNPY_OK;
+}
+
+static i64 dd_ragged_pair_bytes(i64 N, i64 M) {
+    i64 w = align_up(14 * N * 8, 256);        // compressed words
+    i64 fi = align_up(N * 4, 256);            // rank -> frame
+    i64 p = align_up(7 * M * 8, 256);         // per-series power spectra
+    i64 acf = align_up(7 * N * 8, 256);       // per-series ACFs
+    i64 small = 7 * 8 * 2 + 16 + 256;         // lens, scale, bias
+    return w + fi + p + acf + small;
+}
+int64_t dynpy_dd_ragged_workspace_bytes(int64_t n_frames, int64_t M, int64_t pairs) {
+    if (pairs < 1) pairs = 1;
+    i64 t = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;  // T for >= 14 transforms in flight
+    return pairs * dd_ragged_pair_bytes(n_frames, M) + t + 4096;
+}
+
+int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                                     const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
+                                     double rmax, double* G, int64_t M, void* ws, int64_t ws_bytes,
+                                     dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_M(M, n_frames);
+    if (rc) return rc;
+    if (!coords || !pair_i || !pair_j || !G || n_pairs < 0 || n_atoms < 1 || !ws) {
+        set_error("dynpy_dd_pairs_ragged_to_acf_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n_pairs == 0) return DYNPY_OK;
+    DeviceState* d;
+    rc = get_device_state(&d, st);
+    if (rc) return rc;
+    const i64 N = n_frames;
+    const i64 tbytes = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;
+    i64 cap = (ws_bytes - tbytes - 4096) / dd_ragged_pair_bytes(N, M);
+    if (cap < 1) {
+        set_error("dynpy_dd_pairs_ragged_to_acf_f64: workspace too small (need >= %lld bytes)",
+                  (long long)dynpy_dd_ragged_workspace_bytes(N, M, 1));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    if (cap > n_pairs) cap = n_pairs;
+    char* base = (char*)ws;
+    i64 off = 0;
+    auto carve = [&](i64 bytes) { char* p = base + off; off += align_up(bytes, 256); return p; };
+    i64* lens = (i64*)carve(cap * 7 * 8);
+    double* scale = (double*)carve(cap * 7 * 8);
+    double* bias = (double*)carve(cap * 16);
+    int* fidx = (int*)carve(cap * N * 4);
+    double* W = (double*)carve(cap * 14 * N * 8);
+    double* P = (double*)carve(cap * 7 * M * 8);
+    double* acf = (double*)carve(cap * 7 * N * 8);
+    cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
+    const i64 T_cap = tbytes ? 14 : 0;
+
+    for (i64 p0 = 0; p0 < n_pairs; p0 += cap) {
+        const i64 cnt = n_pairs - p0 < cap ? n_pairs - p0 : cap;
+        DYNPY_CHECK(launch_dd_ragged_words(coords, N, pair_i, pair_j, p0, cnt, a, b, c, rmax, W, fidx, lens, scale,
+                                           bias, st), "dd ragged words");
+        PlanarLoader ld;
+        memset(&ld, 0, sizeof(ld));
+        ld.re = W;
+        ld.im = W + N;
+        ld.hi = 14 * N;
+        ld.lo = 2 * N;
+        ld.n_im_valid = (i64)1 << 62;
+        ld.nslots = 7;
+        ld.N = N;
+        ld.lens = lens;
+        ld.bias = bias;
+        ld.bias_slot = 3;
+        EpiParams ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.out = P;
+        ep.M = M;
+        ep.nslots = 7;
+        DYNPY_CHECK(forward_planar_power(ld, ep, cnt * 7, M, 7, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged forward");
+        SpectrumLoader sl;
+        sl.S = P;
+        sl.M = M;
+        sl.M1 = M > DYNPY_ROW_LEN ? (int)(M / DYNPY_ROW_LEN) : 1;
+        EpiParams e2;
+        memset(&e2, 0, sizeof(e2));
+        e2.out = acf;
+        e2.M = M;
+        e2.nslots = 1;
+        e2.n_out = N;
+        e2.scale = 1.0 / (double)M;
+        DYNPY_CHECK(forward_spectrum_real(sl, e2, cnt * 7, M, 1, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged inverse");
+        DYNPY_CHECK(launch_dd_ragged_scatter(acf, fidx, lens, N, cnt * 7, G, st), "dd ragged scatter");
+    }
+    return DYNPY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SR
+int dynpy_sr_angmom_f64(const double* pos, const double* vel, int64_t n_atoms, int64_t n_frames,
+                        const int32_t* mol_atoms, int64_t n_mol, int n_at_mol, const double* mass,
+                        const int32_t* axis_atoms, int axis_rule, double a, double b, double c, double inv_dt,
+                        double* J, double* omega, double* axes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!pos || !mol_atoms || !mass || !axis_atoms || n_mol < 0 || n_at_mol < 1 || n_frames < (vel ? 1 : 2) ||
+        (axis_rule != 0 && axis_rule != 1) || n_atoms < 1) {
+        set_error("dynpy_sr_angmom_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_sr_angmom(pos, vel, n_frames, mol_atoms, n_mol, n_at_mol, mass, axis_atoms, axis_rule, a, b, c,
+                                 inv_dt, J, omega, axes, st), "sr angmom");
+    return DYNPY_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Simpson
+int dynpy_simpson_f64(const double* y, const double* x, int64_t n, int n_cols, int64_t col_stride, int mode,
+                      double* out, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || !x || !out || n < 1 || n_cols < 0 || col_stride < n || (mode != 0 && mode != 1)) {
+        set_error("dynpy_simpson_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_simpson(y, x, n, n_cols, col_stride, mode, out, st), "simpson");
+    return DYNPY_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,664 @@
+// dynpy_b200 — non-FFT kernels of the hot path (sm_100a): coordinate wrap, bit-exact
+// pdist_ortho, dipolar word generator, pair presence count, spin-rotation angular momentum,
+// Simpson reduction.  Reference lines are cited per kernel.
+#include "kernels.h"
+
+namespace dynpy {
+
+// ------------------------------------------------------------------ twiddle table
+__global__ void k_init_twiddles(double2* tw) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 4096) {
+        double s, c;
+        sincospi(2.0 * (double)j / 4096.0, &s, &c);
+        tw[j] = make_double2(c, -s);
+    }
+}
+cudaError_t launch_init_twiddles(double2* tw, cudaStream_t st) {
+    k_init_twiddles<<<16, 256, 0, st>>>(tw);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ wrap
+// np.mod(x, L) (universe.py:301-304 via distances.modv): C fmod, then the sign fix-up numpy
+// applies (npy_divmod): a non-zero remainder with the wrong sign gets +L (may round to L).
+__device__ __forceinline__ double np_mod(double x, double L) {
+    double m = fmod(x, L);
+    if (m != 0.0) {
+        if ((L < 0.0) != (m < 0.0)) m = __dadd_rn(m, L);
+    } else {
+        m = copysign(0.0, L);
+    }
+    return m;
+}
+__global__ void k_wrap(const double* __restrict__ x, double* __restrict__ out, i64 n, double L) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = np_mod(x[i], L);
+}
+cudaError_t launch_wrap(const double* x, double* out, i64 n, double L, int n_sm, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > (i64)n_sm * 16) blocks = (i64)n_sm * 16;
+    k_wrap<<<(unsigned)blocks, 256, 0, st>>>(x, out, n, L);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ minimum image
+// Literal restatement of the candidate loop of pdist_ortho (distances.py:203-233): 27 images
+// in (aa,bb,cc) order, pxi = xi + aa*a, d = pxi - xj, r2 = dx*dx + dy*dy + dz*dz left to
+// right, strict '<' against a running best that starts at dmax^2.  __d*_rn blocks FMA
+// contraction so every comparison sees the same bits numba/LLVM produces.
+struct MinImage {
+    double dx, dy, dz, r2;
+    int prj;
+    bool found;
+};
+__device__ __forceinline__ MinImage min_image27(double xi, double yi, double zi, double xj, double yj, double zj,
+                                                double a, double b, double c, double dmax2) {
+    MinImage r;
+    r.dx = r.dy = r.dz = 0.0;
+    r.r2 = dmax2;
+    r.prj = 0;
+    r.found = false;
+    int prj = 0;
+#pragma unroll
+    for (int aa = -1; aa <= 1; ++aa) {
+        const double dpx = __dsub_rn(__dadd_rn(xi, __dmul_rn((double)aa, a)), xj);
+        const double sx = __dmul_rn(dpx, dpx);
+#pragma unroll
+        for (int bb = -1; bb <= 1; ++bb) {
+            const double dpy = __dsub_rn(__dadd_rn(yi, __dmul_rn((double)bb, b)), yj);
+            const double sxy = __dadd_rn(sx, __dmul_rn(dpy, dpy));
+#pragma unroll
+            for (int cc = -1; cc <= 1; ++cc) {
+                const double dpz = __dsub_rn(__dadd_rn(zi, __dmul_rn((double)cc, c)), zj);
+                const double r2 = __dadd_rn(sxy, __dmul_rn(dpz, dpz));
+                if (r2 < r.r2) {
+                    r.dx = dpx; r.dy = dpy; r.dz = dpz; r.r2 = r2; r.prj = prj; r.found = true;
+                }
+                ++prj;
+            }
+        }
+    }
+    return r;
+}
+
+// Per-axis form used inside the fused dipolar generator: the minimum over the 27 sums equals
+// the sum of the per-axis minima bit for bit (fp add is monotone), so presence (r2 < rmax^2)
+// and dr are identical to min_image27; only the image picked under an exact rounding tie
+// of the 27 sums could differ.
+__device__ __forceinline__ void axis_min(double xi, double xj, double a, double& d, double& d2) {
+    const double dm = __dsub_rn(__dsub_rn(xi, a), xj);
+    const double d0 = __dsub_rn(xi, xj);
+    const double dp = __dsub_rn(__dadd_rn(xi, a), xj);
+    const double sm = __dmul_rn(dm, dm), s0 = __dmul_rn(d0, d0), sp = __dmul_rn(dp, dp);
+    d = dm; d2 = sm;
+    if (s0 < d2) { d = d0; d2 = s0; }
+    if (sp < d2) { d = dp; d2 = sp; }
+}
+
+// ------------------------------------------------------------------ pdist_ortho (bit-exact)
+__device__ __forceinline__ void pair_from_linear(i64 p, i64 n, i64& i, i64& j) {
+    // row-major upper triangle: row i starts at i*n - i*(i+1)/2
+    double nn = (double)n;
+    i64 ii = (i64)floor(((2.0 * nn - 1.0) - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * (double)p)) * 0.5);
+    if (ii < 0) ii = 0;
+    if (ii > n - 2) ii = n - 2;
+    while (ii > 0 && ii * n - ii * (ii + 1) / 2 > p) --ii;
+    while ((ii + 1) * n - (ii + 1) * (ii + 2) / 2 <= p) ++ii;
+    i = ii;
+    j = p - (ii * n - ii * (ii + 1) / 2) + ii + 1;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_pdist(const double* __restrict__ ux, const double* __restrict__ uy, const double* __restrict__ uz, i64 stride,
+        i64 n, double a, double b, double c, const i64* __restrict__ index, double dmax2, i64 npairs,
+        i64* __restrict__ block_counts, double* dx, double* dy, double* dz, double* dr, i64* a0, i64* a1,
+        i64* prj) {
+    __shared__ int warp_cnt[8];
+    const i64 p = (i64)blockIdx.x * 256 + threadIdx.x;
+    MinImage r;
+    r.found = false;
+    i64 i = 0, j = 0;
+    if (p < npairs) {
+        pair_from_linear(p, n, i, j);
+        r = min_image27(ux[i * stride], uy[i * stride], uz[i * stride], ux[j * stride], uy[j * stride],
+                        uz[j * stride], a, b, c, dmax2);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, r.found);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (!WRITE) {
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+            block_counts[blockIdx.x] = t;
+        }
+    } else {
+        if (r.found) {
+            i64 off = block_counts[blockIdx.x];  // exclusive prefix of this block
+            for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+            off += __popc(ball & ((1u << lane) - 1u));
+            dx[off] = r.dx; dy[off] = r.dy; dz[off] = r.dz;
+            dr[off] = sqrt(r.r2);  // np.sqrt(dpr_) (distances.py:225): correctly rounded in both
+            a0[off] = index[i]; a1[off] = index[j]; prj[off] = r.prj;
+        }
+    }
+}
+
+// exclusive scan of block counts by one CTA; total -> *count
+__global__ void k_scan_counts(i64* __restrict__ v, i64 n, i64* __restrict__ count) {
+    __shared__ i64 sh[1024];
+    __shared__ i64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 base = 0; base < n; base += 1024) {
+        i64 idx = base + threadIdx.x;
+        i64 x = idx < n ? v[idx] : 0;
+        sh[threadIdx.x] = x;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            i64 t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        i64 incl = sh[threadIdx.x];
+        if (idx < n) v[idx] = carry + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
+}
+
+cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i64 stride, i64 n, double a,
+                         double b, double c, const i64* index, double dmax, double* dx, double* dy, double* dz,
+                         double* dr, i64* a0, i64* a1, i64* prj, i64* count, i64* block_counts,
+                         cudaStream_t st) {
+    const i64 npairs = n * (n - 1) / 2;
+    if (npairs <= 0) return cudaMemsetAsync(count, 0, sizeof(i64), st);
+    const i64 nblocks = (npairs + 255) / 256;
+    const double dmax2 = dmax * dmax;  // dmax**2 (distances.py:177)
+    k_pdist<false><<<(unsigned)nblocks, 256, 0, st>>>(ux, uy, uz, stride, n, a, b, c, index, dmax2, npairs,
+                                                     block_counts, dx, dy, dz, dr, a0, a1, prj);
+    k_scan_counts<<<1, 1024, 0, st>>>(block_counts, nblocks, count);
+    k_pdist<true><<<(unsigned)nblocks, 256, 0, st>>>(ux, uy, uz, stride, n, a, b, c, index, dmax2, npairs,
+                                                    block_counts, dx, dy, dz, dr, a0, a1, prj);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ dipolar words
+// ddrax.py:72-126 in Cartesian closed form (no arccos/atan2/sincos):
+//   Y20 = 1/4 sqrt(5/pi) (3 z^2/r^2 - 1)
+//   Y21 = -1/2 sqrt(15/2pi) z (x + i y)/r^2        Y22 = 1/4 sqrt(15/2pi) (x + i y)^2/r^2
+//   r^-3 ;  F2m = sqrt(4 pi/5) Y2m r^-3
+struct DDWords {
+    double y20, y21r, y21i, y22r, y22i, r3, f20, f21r, f21i, f22r, f22i;
+};
+__device__ __forceinline__ DDWords dd_words(double dx, double dy, double dz, double r2) {
+    const double C20 = 0.31539156525252000603;   // (1/4) sqrt(5/pi)
+    const double C21 = -0.77254840404638362;     // -(1/2) sqrt(15/(2 pi))
+    const double C22 = 0.38627420202319181;      // (1/4) sqrt(15/(2 pi))
+    const double KF = 1.5853309190424043;        // sqrt(4 pi/5)
+    DDWords w;
+    double rinv = rsqrt(r2);
+    rinv = rinv * fma(-0.5 * r2, rinv * rinv, 1.5);  // one Newton step: r^-1 to ~1 ulp
+    const double ir2 = rinv * rinv;
+    w.r3 = ir2 * rinv;
+    w.y20 = C20 * (3.0 * dz * dz * ir2 - 1.0);
+    const double zr = dz * ir2;
+    w.y21r = C21 * zr * dx;
+    w.y21i = C21 * zr * dy;
+    w.y22r = C22 * (dx * dx - dy * dy) * ir2;
+    w.y22i = C22 * 2.0 * dx * dy * ir2;
+    const double k = KF * w.r3;
+    w.f20 = k * w.y20; w.f21r = k * w.y21r; w.f21i = k * w.y21i; w.f22r = k * w.y22r; w.f22i = k * w.y22i;
+    return w;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;  // valid in thread 0
+}
+
+// grid (ceil(N/256), items): thread = one frame of pair-pair `item` (pairs 2*item, 2*item+1).
+// Z[item][slot][2][N] planar; slots documented in kernels.h (DD_NSLOTS = 11).
+__global__ void __launch_bounds__(256)
+k_dd_words(const double* __restrict__ X, i64 A, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
+           i64 pair0, i64 n_pairs, double a, double b, double c, double* __restrict__ Z,
+           double* __restrict__ bias) {
+    __shared__ double sh[8];
+    const i64 item = blockIdx.y;
+    const i64 n = (i64)blockIdx.x * 256 + threadIdx.x;
+    double* z = Z + item * (i64)(DD_NSLOTS * 2) * N;
+    double rsum[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const i64 p = pair0 + 2 * item + h;
+        DDWords w;
+        bool ok = (p < n_pairs) && (n < N);
+        if (ok) {
+            const i64 i = pi[p], j = pj[p];
+            const double* xi = X + i * 3 * N;
+            const double* xj = X + j * 3 * N;
+            double dx, dy, dz, sx, sy, sz;
+            axis_min(__ldg(xi + n), __ldg(xj + n), a, dx, sx);
+            axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, dy, sy);
+            axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, dz, sz);
+            const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+            w = dd_words(dx, dy, dz, r2);
+            rsum[h] = w.r3;
+        } else {
+            w.y20 = w.y21r = w.y21i = w.y22r = w.y22i = w.r3 = w.f20 = w.f21r = w.f21i = w.f22r = w.f22i = 0.0;
+        }
+        if (n < N) {
+            // packed real series: plane h of slots 0 (Y20), 5 (r^-3), 6 (F20)
+            z[(0 * 2 + h) * N + n] = w.y20;
+            z[(5 * 2 + h) * N + n] = w.r3;
+            z[(6 * 2 + h) * N + n] = w.f20;
+            // complex series of pair h: slots 1+h (Y21), 3+h (Y22), 7+h (F21), 9+h (F22)
+            z[((1 + h) * 2 + 0) * N + n] = w.y21r; z[((1 + h) * 2 + 1) * N + n] = w.y21i;
+            z[((3 + h) * 2 + 0) * N + n] = w.y22r; z[((3 + h) * 2 + 1) * N + n] = w.y22i;
+            z[((7 + h) * 2 + 0) * N + n] = w.f21r; z[((7 + h) * 2 + 1) * N + n] = w.f21i;
+            z[((9 + h) * 2 + 0) * N + n] = w.f22r; z[((9 + h) * 2 + 1) * N + n] = w.f22i;
+        }
+    }
+    const double s0 = block_sum_256(rsum[0], sh);
+    const double s1 = block_sum_256(rsum[1], sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(bias + 2 * item, s0);
+        atomicAdd(bias + 2 * item + 1, s1);
+    }
+}
+cudaError_t launch_dd_words(const double* X, i64 A, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs,
+                            i64 items, double a, double b, double c, double* Z, double* bias, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(bias, 0, sizeof(double) * 2 * items, st);
+    if (e != cudaSuccess) return e;
+    for (i64 it0 = 0; it0 < items; it0 += 32768) {
+        i64 cnt = items - it0 < 32768 ? items - it0 : 32768;
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)cnt);
+        k_dd_words<<<grid, 256, 0, st>>>(X, A, N, pi, pj, pair0 + 2 * it0, n_pairs, a, b, c,
+                                         Z + it0 * (i64)(DD_NSLOTS * 2) * N, bias + 2 * it0);
+    }
+    return cudaGetLastError();
+}
+
+// frames with r2 < rmax^2 per pair: one CTA per pair
+__global__ void __launch_bounds__(256)
+k_dd_pair_count(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
+                double a, double b, double c, double rmax2, i64* __restrict__ counts) {
+    __shared__ double sh[8];
+    const i64 p = blockIdx.x;
+    const double* xi = X + (i64)pi[p] * 3 * N;
+    const double* xj = X + (i64)pj[p] * 3 * N;
+    double cnt = 0.0;
+    for (i64 n = threadIdx.x; n < N; n += 256) {
+        double d, sx, sy, sz;
+        axis_min(__ldg(xi + n), __ldg(xj + n), a, d, sx);
+        axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, d, sy);
+        axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, d, sz);
+        if (__dadd_rn(__dadd_rn(sx, sy), sz) < rmax2) cnt += 1.0;
+    }
+    const double t = block_sum_256(cnt, sh);
+    if (threadIdx.x == 0) counts[p] = (i64)t;
+}
+cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
+                                 double b, double c, double rmax, i64* counts, cudaStream_t st) {
+    if (n_pairs <= 0) return cudaSuccess;
+    k_dd_pair_count<<<(unsigned)n_pairs, 256, 0, st>>>(X, N, pi, pj, a, b, c, rmax * rmax, counts);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ ragged dipolar series
+// One CTA per pair: compress the frames in which the pair is present (r2 < rmax^2) into 7
+// complex series of length N_p (Y20, Y21, Y22, r^-3, F20, F21, F22; real ones with zero
+// imaginary plane) and record rank -> frame.  W[pair][7][2][N], fidx[pair][N], lens[7*pair+s].
+__global__ void __launch_bounds__(256)
+k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
+                  i64 pair0, double a, double b, double c, double rmax2, double* __restrict__ W,
+                  int* __restrict__ fidx, i64* __restrict__ lens, double* __restrict__ scale,
+                  double* __restrict__ bias) {
+    __shared__ int wcnt[8];
+    __shared__ i64 base;
+    __shared__ double sh[8];
+    const i64 pl = blockIdx.x;
+    const i64 p = pair0 + pl;
+    const double* xi = X + (i64)pi[p] * 3 * N;
+    const double* xj = X + (i64)pj[p] * 3 * N;
+    double* w = W + pl * 14 * N;
+    int* fi = fidx + pl * N;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    double rsum = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (i64 n0 = 0; n0 < N; n0 += 256) {
+        const i64 n = n0 + threadIdx.x;
+        bool ok = false;
+        DDWords d;
+        if (n < N) {
+            double dx, dy, dz, sx, sy, sz;
+            axis_min(__ldg(xi + n), __ldg(xj + n), a, dx, sx);
+            axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, dy, sy);
+            axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, dz, sz);
+            const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+            ok = r2 < rmax2;
+            if (ok) d = dd_words(dx, dy, dz, r2);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) wcnt[warp] = __popc(ball);
+        __syncthreads();
+        if (ok) {
+            i64 off = base;
+            for (int q = 0; q < warp; ++q) off += wcnt[q];
+            off += __popc(ball & ((1u << lane) - 1u));
+            fi[off] = (int)n;
+            w[0 * N + off] = d.y20;  w[1 * N + off] = 0.0;
+            w[2 * N + off] = d.y21r; w[3 * N + off] = d.y21i;
+            w[4 * N + off] = d.y22r; w[5 * N + off] = d.y22i;
+            w[6 * N + off] = d.r3;   w[7 * N + off] = 0.0;
+            w[8 * N + off] = d.f20;  w[9 * N + off] = 0.0;
+            w[10 * N + off] = d.f21r; w[11 * N + off] = d.f21i;
+            w[12 * N + off] = d.f22r; w[13 * N + off] = d.f22i;
+            rsum += d.r3;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += wcnt[q]; base += t; }
+        __syncthreads();
+    }
+    const double t = block_sum_256(rsum, sh);
+    if (threadIdx.x == 0) {
+        const i64 np = base;
+        for (int s = 0; s < 7; ++s) {
+            lens[pl * 7 + s] = np;
+            scale[pl * 7 + s] = 1.0;
+        }
+        bias[2 * pl] = t;      // sum of r^-3 over present frames (slot 3, re plane)
+        bias[2 * pl + 1] = 0.0;
+    }
+}
+cudaError_t launch_dd_ragged_words(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 npairs,
+                                   double a, double b, double c, double rmax, double* W, int* fidx, i64* lens,
+                                   double* scale, double* bias, cudaStream_t st) {
+    if (npairs <= 0) return cudaSuccess;
+    k_dd_ragged_words<<<(unsigned)npairs, 256, 0, st>>>(X, N, pi, pj, pair0, a, b, c, rmax * rmax, W, fidx, lens,
+                                                        scale, bias);
+    return cudaGetLastError();
+}
+
+// G[acc][fidx[pair][k]] += acf[f][k] / (M * N_p^... ) : scatter of per-pair ACFs to frame bins
+// acf holds Re(FFT(P_f))[k] * (1/M) for k < N (n_out = N); f = pair*7 + acc.
+__global__ void k_dd_ragged_scatter(const double* __restrict__ acf, const int* __restrict__ fidx,
+                                    const i64* __restrict__ lens, i64 N, i64 nfft, double* __restrict__ G) {
+    const i64 f = blockIdx.y;
+    const i64 pl = f / 7;
+    const int acc = (int)(f % 7);
+    const i64 np = lens[f];
+    if (np <= 0) return;
+    const double inv = 1.0 / (double)np;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (i64)gridDim.x * blockDim.x)
+        atomicAdd(G + (i64)acc * N + fidx[pl * N + k], acf[f * N + k] * inv);
+}
+cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 nfft,
+                                     double* G, cudaStream_t st) {
+    if (nfft <= 0) return cudaSuccess;
+    for (i64 f0 = 0; f0 < nfft; f0 += 32767 * 7) {
+        i64 cnt = nfft - f0 < 32767 * 7 ? nfft - f0 : 32767 * 7;
+        int gx = (int)((N + 255) / 256);
+        if (gx > 64) gx = 64;
+        dim3 grid(gx, (unsigned)cnt);
+        k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf + f0 * N, fidx + (f0 / 7) * N, lens + f0, N, cnt, G);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ spin-rotation
+__device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3], double x[3]) {
+    // Gaussian elimination with partial pivoting (what numpy.linalg.solve / LAPACK gesv does)
+    double A[3][3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { b[i] = b_[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[i][j] = A_[i][j]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int piv = k;
+        double best = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) if (fabs(A[i][k]) > best) { best = fabs(A[i][k]); piv = i; }
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) if (piv == i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { double t = A[k][j]; A[k][j] = A[i][j]; A[i][j] = t; }
+            double t = b[k]; b[k] = b[i]; b[i] = t;
+        }
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            const double l = A[i][k] / A[k][k];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) if (j >= k) A[i][j] -= l * A[k][j];
+            b[i] -= l * b[k];
+        }
+    }
+    x[2] = b[2] / A[2][2];
+    x[1] = (b[1] - A[1][2] * x[2]) / A[1][1];
+    x[0] = (b[0] - A[0][1] * x[1] - A[0][2] * x[2]) / A[0][0];
+}
+__device__ __forceinline__ void inv3(const double m[3][3], double o[3][3]) {
+    const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    const double c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2];
+    const double c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    const double det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+    const double id = 1.0 / det;
+    o[0][0] = c00 * id; o[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id; o[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+    o[1][0] = c01 * id; o[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id; o[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+    o[2][0] = c02 * id; o[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id; o[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+}
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void normalize3(double v[3]) {
+    const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] /= n; v[1] /= n; v[2] /= n;
+}
+
+// thread = (frame, molecule); SR_func1 (SRrax.py:438-510):
+//   r, v relative to the mass-weighted mean; R = sum(r^2 1 - r r^T) unweighted; I mass-weighted;
+//   L' = sum r x v unweighted; omega = solve(R, L'); body axes from two minimum-image pair
+//   vectors; omega_b = ax^-1 omega; I_b = ax^-1 I ax; J = I_b omega_b.
+__global__ void __launch_bounds__(128)
+k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 N, const int* __restrict__ mol_atoms,
+            i64 n_mol, int nat, const double* __restrict__ mass, const int* __restrict__ axis_atoms, int axis_rule,
+            double ca, double cb, double cc, double inv_dt, i64 n_out, double* __restrict__ J,
+            double* __restrict__ omega, double* __restrict__ axes) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 m = blockIdx.y;
+    if (t >= n_out) return;
+    const i64 fr = vel ? t : t + 1;  // frame whose positions are used
+    const int* at = mol_atoms + m * nat;
+    double msum = 0.0, cp[3] = {0, 0, 0}, cv[3] = {0, 0, 0};
+    for (int k = 0; k < nat; ++k) {
+        const double* p = pos + (i64)at[k] * 3 * N;
+        const double mk = mass[k];
+        msum += mk;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = p[d * N + fr];
+            const double v = vel ? vel[((i64)at[k] * 3 + d) * N + fr] : (x - p[d * N + fr - 1]) * inv_dt;
+            cp[d] += mk * x; cv[d] += mk * v;
+        }
+    }
+    const double im = 1.0 / msum;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { cp[d] *= im; cv[d] *= im; }
+    double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rv[3] = {0, 0, 0};
+    for (int k = 0; k < nat; ++k) {
+        const double* p = pos + (i64)at[k] * 3 * N;
+        const double mk = mass[k];
+        double r[3], v[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = p[d * N + fr];
+            const double vv = vel ? vel[((i64)at[k] * 3 + d) * N + fr] : (x - p[d * N + fr - 1]) * inv_dt;
+            r[d] = x - cp[d]; v[d] = vv - cv[d];
+        }
+        const double xx = r[0] * r[0], yy = r[1] * r[1], zz = r[2] * r[2];
+        R[0][0] += yy + zz; R[1][1] += xx + zz; R[2][2] += xx + yy;
+        R[0][1] += -r[0] * r[1]; R[0][2] += -r[0] * r[2]; R[1][2] += -r[1] * r[2];
+        I[0][0] += mk * (yy + zz); I[1][1] += mk * (xx + zz); I[2][2] += mk * (xx + yy);
+        I[0][1] += -mk * r[0] * r[1]; I[0][2] += -mk * r[0] * r[2]; I[1][2] += -mk * r[1] * r[2];
+        double c3[3];
+        cross3(r, v, c3);
+        rv[0] += c3[0]; rv[1] += c3[1]; rv[2] += c3[2];
+    }
+    R[1][0] = R[0][1]; R[2][0] = R[0][2]; R[2][1] = R[1][2];
+    I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
+    double o[3];
+    solve3(R, rv, o);
+    // body axes from the two pair vectors (wrapped coordinates, 27-image minimum image)
+    const int* ax4 = axis_atoms + m * 4;
+    double dvec[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const double* pa = pos + (i64)ax4[2 * h] * 3 * N;
+        const double* pb = pos + (i64)ax4[2 * h + 1] * 3 * N;
+        MinImage mi = min_image27(np_mod(pa[fr], ca), np_mod(pa[N + fr], cb), np_mod(pa[2 * N + fr], cc),
+                                  np_mod(pb[fr], ca), np_mod(pb[N + fr], cb), np_mod(pb[2 * N + fr], cc), ca, cb, cc,
+                                  1.0e300);
+        dvec[h][0] = mi.dx; dvec[h][1] = mi.dy; dvec[h][2] = mi.dz;
+    }
+    double X[3], Y[3], Z[3];
+    if (axis_rule == 1) {
+        Z[0] = -(dvec[0][0] + dvec[1][0]); Z[1] = -(dvec[0][1] + dvec[1][1]); Z[2] = -(dvec[0][2] + dvec[1][2]);
+        normalize3(Z);
+        cross3(Z, dvec[0], X); normalize3(X);
+        cross3(Z, X, Y); normalize3(Y);
+    } else {
+        Z[0] = dvec[0][0]; Z[1] = dvec[0][1]; Z[2] = dvec[0][2];
+        normalize3(Z);
+        cross3(Z, dvec[1], X); normalize3(X);
+        cross3(Z, X, Y); normalize3(Y);
+    }
+    double ax[3][3] = {{X[0], Y[0], Z[0]}, {X[1], Y[1], Z[1]}, {X[2], Y[2], Z[2]}};  // columns x,y,z
+    double ai[3][3];
+    inv3(ax, ai);
+    double ob[3], Ia[3][3], Ib[3][3], Jb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ob[i] = ai[i][0] * o[0] + ai[i][1] * o[1] + ai[i][2] * o[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ia[i][j] = ai[i][0] * I[0][j] + ai[i][1] * I[1][j] + ai[i][2] * I[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ib[i][j] = Ia[i][0] * ax[0][j] + Ia[i][1] * ax[1][j] + Ia[i][2] * ax[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Jb[i] = Ib[i][0] * ob[0] + Ib[i][1] * ob[1] + Ib[i][2] * ob[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (J) J[(m * 3 + d) * n_out + t] = Jb[d];
+        if (omega) omega[(m * 3 + d) * n_out + t] = ob[d];
+    }
+    if (axes) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) axes[(m * 9 + i * 3 + j) * n_out + t] = ax[i][j];
+    }
+}
+cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const int* mol_atoms, i64 n_mol, int nat,
+                             const double* mass, const int* axis_atoms, int axis_rule, double a, double b, double c,
+                             double inv_dt, double* J, double* omega, double* axes, cudaStream_t st) {
+    const i64 n_out = vel ? N : N - 1;
+    if (n_out <= 0 || n_mol <= 0) return cudaSuccess;
+    for (i64 m0 = 0; m0 < n_mol; m0 += 65535) {
+        i64 cnt = n_mol - m0 < 65535 ? n_mol - m0 : 65535;
+        dim3 grid((unsigned)((n_out + 127) / 128), (unsigned)cnt);
+        k_sr_angmom<<<grid, 128, 0, st>>>(pos, vel, N, mol_atoms + m0 * nat, cnt, nat, mass, axis_atoms + m0 * 4,
+                                          axis_rule, a, b, c, inv_dt, n_out, J ? J + m0 * 3 * n_out : nullptr,
+                                          omega ? omega + m0 * 3 * n_out : nullptr,
+                                          axes ? axes + m0 * 9 * n_out : nullptr);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ Simpson
+// scipy.integrate.simpson(y, x=x): composite Simpson with the non-uniform-h weights of
+// scipy's _basic_simpson on an odd number of points + the even-N end rule (mode).
+__device__ double simpson_odd_block(const double* __restrict__ y, const double* __restrict__ x, i64 start, i64 npts,
+                                    double* sh) {
+    double acc = 0.0;
+    const i64 nseg = (npts - 1) / 2;
+    for (i64 s = threadIdx.x; s < nseg; s += blockDim.x) {
+        const i64 i0 = start + 2 * s;
+        const double h0 = x[i0 + 1] - x[i0], h1 = x[i0 + 2] - x[i0 + 1];
+        const double hsum = h0 + h1, hprod = h0 * h1;
+        const double h0divh1 = (h1 != 0.0) ? h0 / h1 : 0.0;
+        const double t0 = (h0divh1 != 0.0) ? 1.0 / h0divh1 : 0.0;
+        const double t1 = (hprod != 0.0) ? hsum / hprod : 0.0;
+        acc += hsum / 6.0 * (y[i0] * (2.0 - t0) + y[i0 + 1] * (hsum * t1) + y[i0 + 2] * (2.0 - h0divh1));
+    }
+    // block reduction (blockDim = 1024)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    }
+    return t;  // valid in thread 0
+}
+__global__ void __launch_bounds__(1024)
+k_simpson(const double* __restrict__ Y, const double* __restrict__ x, i64 n, i64 col_stride, int mode,
+          double* __restrict__ out) {
+    __shared__ double sh[32];
+    const double* y = Y + (i64)blockIdx.x * col_stride;
+    double res = 0.0;
+    if (n == 1) {
+        res = 0.0;
+    } else if (n & 1) {
+        res = simpson_odd_block(y, x, 0, n, sh);
+    } else if (n == 2) {
+        res = 0.5 * (x[1] - x[0]) * (y[1] + y[0]);
+    } else if (mode == 1) {
+        const double A = simpson_odd_block(y, x, 0, n - 1, sh);
+        const double B = simpson_odd_block(y, x, 1, n - 1, sh);
+        const double ta = 0.5 * (x[n - 1] - x[n - 2]) * (y[n - 1] + y[n - 2]);
+        const double tb = 0.5 * (x[1] - x[0]) * (y[1] + y[0]);
+        res = 0.5 * ((A + ta) + (B + tb));
+    } else {
+        res = simpson_odd_block(y, x, 0, n - 1, sh);
+        const double h0 = x[n - 2] - x[n - 3], h1 = x[n - 1] - x[n - 2];
+        double den = 6.0 * (h1 + h0);
+        const double alpha = den != 0.0 ? (2.0 * h1 * h1 + 3.0 * h0 * h1) / den : 0.0;
+        den = 6.0 * h0;
+        const double beta = den != 0.0 ? (h1 * h1 + 3.0 * h0 * h1) / den : 0.0;
+        den = 6.0 * h0 * (h0 + h1);
+        const double eta = den != 0.0 ? (h1 * h1 * h1) / den : 0.0;
+        res = res + alpha * y[n - 1] + beta * y[n - 2] - eta * y[n - 3];
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = res;
+}
+cudaError_t launch_simpson(const double* y, const double* x, i64 n, int n_cols, i64 col_stride, int mode,
+                           double* out, cudaStream_t st) {
+    if (n_cols <= 0) return cudaSuccess;
+    k_simpson<<<n_cols, 1024, 0, st>>>(y, x, n, col_stride, mode, out);
+    return cudaGetLastError();
+}
+
+}  // namespace dynpy

@@ -1,0 +1,272 @@
+"""torch-tensor wrappers over the C-ABI (device pointers + the current CUDA stream).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation happens in
+the hand-written kernels behind ``include/dynpy_b200.h``.  All tensors must be CUDA,
+contiguous, float64 / int64 / int32 as documented; there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_WS = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DynpyError("%s must be a CUDA tensor (dynpy_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise _lib.DynpyError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.DynpyError("%s must be contiguous" % name)
+    return t
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (uint8)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WS.pop(key, None)
+        buf = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % key)
+        _WS[key] = buf
+    return buf
+
+
+def release_workspace():
+    _WS.clear()
+
+
+def sm_count() -> int:
+    n = _lib.load().dynpy_device_sm_count()
+    if n < 0:
+        _lib.check(n, "dynpy_device_sm_count")
+    return n
+
+
+def fft_length(n: int) -> int:
+    return int(_lib.load().dynpy_fft_length(int(n)))
+
+
+def _fft_ws(M: int, n_fft: int, device, budget: int = 2 << 30):
+    lib = _lib.load()
+    one = lib.dynpy_fft_workspace_bytes(M, 1)
+    if one == 0:
+        return None, 0
+    n = max(1, min(n_fft, budget // one))
+    ws = workspace(device, n * one)
+    return ws, ws.numel()
+
+
+# ------------------------------------------------------------------------------ WK
+def wk_acf_sum(re, im=None, pack_real_pairs=False, scale=None, M=None, spectrum=None):
+    """spectrum[M] += sum_s |FFT_M(series_s)|^2 for series ``re[s] (+ i im[s])`` of shape [S, N]."""
+    lib = _lib.load()
+    re = _chk(re, torch.float64, "re")
+    S, N = re.shape
+    if im is not None:
+        im = _chk(im, torch.float64, "im")
+        assert im.shape == re.shape
+    if scale is not None:
+        scale = _chk(scale, torch.float64, "scale")
+    M = fft_length(N) if M is None else int(M)
+    if spectrum is None:
+        spectrum = torch.zeros(M, dtype=torch.float64, device=re.device)
+    _chk(spectrum, torch.float64, "spectrum")
+    with torch.cuda.device(re.device):
+        n_fft = (S + 1) // 2 if pack_real_pairs else S
+        ws, wsb = _fft_ws(M, n_fft, re.device)
+        rc = lib.dynpy_wk_acf_sum_f64(re.data_ptr(), im.data_ptr() if im is not None else None, S, N, N,
+                                      1 if pack_real_pairs else 0, scale.data_ptr() if scale is not None else None,
+                                      spectrum.data_ptr(), M, ws.data_ptr() if ws is not None else None, wsb, _stream())
+    _lib.check(rc, "dynpy_wk_acf_sum_f64")
+    return spectrum
+
+
+def ifft_acf(spectrum, n_out: int, scale: float):
+    """acf[a, k] = scale * Re(FFT_M(spectrum[a]))[k], k < n_out."""
+    lib = _lib.load()
+    spectrum = _chk(spectrum, torch.float64, "spectrum")
+    if spectrum.dim() == 1:
+        spectrum = spectrum[None]
+    n_acc, M = spectrum.shape
+    acf = torch.empty((n_acc, n_out), dtype=torch.float64, device=spectrum.device)
+    with torch.cuda.device(spectrum.device):
+        ws, wsb = _fft_ws(M, n_acc, spectrum.device)
+        rc = lib.dynpy_ifft_acf_f64(spectrum.data_ptr(), n_acc, M, acf.data_ptr(), int(n_out), float(scale),
+                                    ws.data_ptr() if ws is not None else None, wsb, _stream())
+    _lib.check(rc, "dynpy_ifft_acf_f64")
+    return acf
+
+
+# ------------------------------------------------------------------------------ QR
+def qr_efg_to_spectrum(efg, M=None, spectrum=None):
+    """efg [S, 6, N] (Vxx,Vyy,Vzz,Vxy,Vxz,Vyz) -> spectrum [3, M] (R20, R2+-1, R2+-2), accumulated."""
+    lib = _lib.load()
+    efg = _chk(efg, torch.float64, "efg")
+    S, six, N = efg.shape
+    assert six == 6
+    M = fft_length(N) if M is None else int(M)
+    if spectrum is None:
+        spectrum = torch.zeros((3, M), dtype=torch.float64, device=efg.device)
+    _chk(spectrum, torch.float64, "spectrum")
+    with torch.cuda.device(efg.device):
+        ws, wsb = _fft_ws(M, 5 * ((S + 1) // 2), efg.device)
+        rc = lib.dynpy_qr_efg_to_spectrum_f64(efg.data_ptr(), S, N, spectrum.data_ptr(), M,
+                                              ws.data_ptr() if ws is not None else None, wsb, _stream())
+    _lib.check(rc, "dynpy_qr_efg_to_spectrum_f64")
+    return spectrum
+
+
+# ------------------------------------------------------------------------------ DD
+def wrap(x, L: float, out=None):
+    lib = _lib.load()
+    x = _chk(x, torch.float64, "x")
+    out = torch.empty_like(x) if out is None else _chk(out, torch.float64, "out")
+    with torch.cuda.device(x.device):
+        rc = lib.dynpy_wrap_f64(x.data_ptr(), out.data_ptr(), x.numel(), float(L), _stream())
+    _lib.check(rc, "dynpy_wrap_f64")
+    return out
+
+
+def pdist_ortho(ux, uy, uz, a, b, c, index, dmax=8.0, stride=1):
+    """Bit-exact distances.pdist_ortho for one frame -> (dx, dy, dz, dr, atom0, atom1, projection)."""
+    lib = _lib.load()
+    for t, nm in ((ux, "ux"), (uy, "uy"), (uz, "uz")):
+        if not t.is_cuda or t.dtype != torch.float64:
+            raise _lib.DynpyError("%s must be a CUDA float64 tensor" % nm)
+    index = _chk(index, torch.int64, "index")
+    n = index.numel()
+    nn = n * (n - 1) // 2
+    dev = index.device
+    f = [torch.empty(max(nn, 1), dtype=torch.float64, device=dev) for _ in range(4)]
+    g = [torch.empty(max(nn, 1), dtype=torch.int64, device=dev) for _ in range(3)]
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        wsb = int(lib.dynpy_pdist_workspace_bytes(n))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        rc = lib.dynpy_pdist_ortho_f64(ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), int(stride), n, float(a), float(b),
+                                       float(c), index.data_ptr(), float(dmax), f[0].data_ptr(), f[1].data_ptr(),
+                                       f[2].data_ptr(), f[3].data_ptr(), g[0].data_ptr(), g[1].data_ptr(),
+                                       g[2].data_ptr(), cnt.data_ptr(), ws.data_ptr(), wsb, _stream())
+    _lib.check(rc, "dynpy_pdist_ortho_f64")
+    k = int(cnt.item())
+    return tuple(t[:k] for t in f) + tuple(t[:k] for t in g)
+
+
+def dd_pair_count(coords, pair_i, pair_j, cell, rmax):
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    pair_i = _chk(pair_i, torch.int32, "pair_i")
+    pair_j = _chk(pair_j, torch.int32, "pair_j")
+    A, three, F = coords.shape
+    counts = torch.empty(pair_i.numel(), dtype=torch.int64, device=coords.device)
+    with torch.cuda.device(coords.device):
+        rc = lib.dynpy_dd_pair_count_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), pair_i.numel(),
+                                         float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
+                                         counts.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_dd_pair_count_f64")
+    return counts
+
+
+def dd_pairs_to_spectrum(coords, pair_i, pair_j, cell, M=None, spectrum=None, ws_budget: int = 4 << 30):
+    """Fused dipolar path for always-present pairs: wrapped coords [A,3,F] -> spectrum [7, M]."""
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    pair_i = _chk(pair_i, torch.int32, "pair_i")
+    pair_j = _chk(pair_j, torch.int32, "pair_j")
+    A, three, F = coords.shape
+    M = fft_length(F) if M is None else int(M)
+    if spectrum is None:
+        spectrum = torch.zeros((7, M), dtype=torch.float64, device=coords.device)
+    _chk(spectrum, torch.float64, "spectrum")
+    npairs = pair_i.numel()
+    items = (npairs + 1) // 2
+    per = int(lib.dynpy_dd_workspace_bytes(F, M, 1))
+    n = max(1, min(items, ws_budget // per))
+    with torch.cuda.device(coords.device):
+        wsb = int(lib.dynpy_dd_workspace_bytes(F, M, n))
+        ws = workspace(coords.device, wsb)
+        rc = lib.dynpy_dd_pairs_to_spectrum_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), npairs,
+                                                float(cell[0]), float(cell[1]), float(cell[2]), spectrum.data_ptr(), M,
+                                                ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dynpy_dd_pairs_to_spectrum_f64")
+    return spectrum
+
+
+def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 2 << 30):
+    """Ragged dipolar path: G[7, F] += per-pair ACFs binned at the k-th present frame."""
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    pair_i = _chk(pair_i, torch.int32, "pair_i")
+    pair_j = _chk(pair_j, torch.int32, "pair_j")
+    A, three, F = coords.shape
+    M = fft_length(F) if M is None else int(M)
+    if G is None:
+        G = torch.zeros((7, F), dtype=torch.float64, device=coords.device)
+    _chk(G, torch.float64, "G")
+    npairs = pair_i.numel()
+    one = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 1))
+    two = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 2))
+    per = two - one
+    n = max(1, min(npairs, (ws_budget - (one - per)) // per))
+    with torch.cuda.device(coords.device):
+        wsb = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, n))
+        ws = workspace(coords.device, wsb)
+        rc = lib.dynpy_dd_pairs_ragged_to_acf_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), npairs,
+                                                  float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
+                                                  G.data_ptr(), M, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dynpy_dd_pairs_ragged_to_acf_f64")
+    return G
+
+
+# ------------------------------------------------------------------------------ SR
+def sr_angmom(pos, mol_atoms, mass, axis_atoms, axis_rule, cell, inv_dt, vel=None, want_omega=True, want_axes=True):
+    """pos [A,3,F] raw -> J [nmol,3,Fo] (+ omega [nmol,3,Fo], axes [nmol,9,Fo]); Fo = F-1 without vel."""
+    lib = _lib.load()
+    pos = _chk(pos, torch.float64, "pos")
+    mol_atoms = _chk(mol_atoms, torch.int32, "mol_atoms")
+    axis_atoms = _chk(axis_atoms, torch.int32, "axis_atoms")
+    mass = _chk(mass, torch.float64, "mass")
+    if vel is not None:
+        vel = _chk(vel, torch.float64, "vel")
+    A, three, F = pos.shape
+    nmol, nat = mol_atoms.shape
+    Fo = F if vel is not None else F - 1
+    dev = pos.device
+    J = torch.empty((nmol, 3, Fo), dtype=torch.float64, device=dev)
+    om = torch.empty((nmol, 3, Fo), dtype=torch.float64, device=dev) if want_omega else None
+    ax = torch.empty((nmol, 9, Fo), dtype=torch.float64, device=dev) if want_axes else None
+    with torch.cuda.device(dev):
+        rc = lib.dynpy_sr_angmom_f64(pos.data_ptr(), vel.data_ptr() if vel is not None else None, A, F,
+                                     mol_atoms.data_ptr(), nmol, nat, mass.data_ptr(), axis_atoms.data_ptr(),
+                                     int(axis_rule), float(cell[0]), float(cell[1]), float(cell[2]), float(inv_dt),
+                                     J.data_ptr(), om.data_ptr() if om is not None else None,
+                                     ax.data_ptr() if ax is not None else None, _stream())
+    _lib.check(rc, "dynpy_sr_angmom_f64")
+    return J, om, ax
+
+
+# ------------------------------------------------------------------------------ Simpson
+SIMPSON_MODES = {"cartwright": 0, "avg": 1}
+
+
+def simpson(y, x, mode="cartwright"):
+    """scipy.integrate.simpson(y[c], x=x) for every row c of y [cols, n] -> tensor [cols]."""
+    lib = _lib.load()
+    y = _chk(y, torch.float64, "y")
+    x = _chk(x, torch.float64, "x")
+    if y.dim() == 1:
+        y = y[None]
+    cols, n = y.shape
+    out = torch.empty(cols, dtype=torch.float64, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = lib.dynpy_simpson_f64(y.data_ptr(), x.data_ptr(), n, cols, n, SIMPSON_MODES[mode], out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_simpson_f64")
+    return out

@@ -1,0 +1,155 @@
+/* dynpy_b200 — C-ABI of the B200-native correlation-function hot path of DynPy.
+ *
+ * The reference (jautschbach/dynpy) is pure Python and has no FFI of its own; the
+ * boundary is a handful of Python call sites.  Each entry point below
+ * names the reference call site(s) it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - fp64 / int64 / int32 exactly as declared; no torch types cross this boundary;
+ *   - `stream` is a cudaStream_t (0 = legacy default stream); calls are asynchronous
+ *     with respect to the host unless stated otherwise, re-entrant per stream;
+ *   - return value: 0 ok, <0 error (DYNPY_ERR_*); dynpy_last_error() gives the text;
+ *   - no C++ exception crosses the ABI; one process per GPU for multi-GPU use.
+ *
+ * Trajectory layout:  coords[atom][axis][frame]  (frame contiguous), bohr.
+ * EFG layout:         efg[nucleus][comp][frame], comp = Vxx,Vyy,Vzz,Vxy,Vxz,Vyz.
+ * Spectrum layout:    accumulated |X|^2 in the engine's internal order (only
+ *                     dynpy_ifft_acf_f64 interprets it); several accumulators are
+ *                     stored back to back, M doubles each.
+ */
+#ifndef DYNPY_B200_H
+#define DYNPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNPY_OK 0
+#define DYNPY_ERR_INVALID (-1)
+#define DYNPY_ERR_LAUNCH (-2)
+#define DYNPY_ERR_WORKSPACE (-3)
+#define DYNPY_ERR_NO_DEVICE (-4)
+
+#define DYNPY_SIMPSON_CARTWRIGHT 0 /* scipy >= 1.11 (even N: Cartwright end correction) */
+#define DYNPY_SIMPSON_AVG 1        /* scipy < 1.11 even='avg' (reproduces the shipped golden file) */
+
+#define DYNPY_AXIS_METHANE 0 /* z = d0/|d0|, x = z x d1, y = z x x   (SRrax.py:389-395, also methyl/ring) */
+#define DYNPY_AXIS_WATER 1   /* Z = -(d0+d1)/|.|, X = Z x d0, Y = Z x X (SRrax.py:397-404) */
+
+typedef void* dynpy_stream_t; /* cudaStream_t */
+
+int dynpy_version(void);
+const char* dynpy_last_error(void);
+/* number of SMs of the current device (grids are sized in multiples of it); <0 on error */
+int dynpy_device_sm_count(void);
+
+/* Padded transform length used for a series of n samples: max(32, 2^ceil(log2(2n))).
+ * Any M >= 2n-1 gives the same linear ACF as the reference's n=2N (qrax.py:153). */
+int64_t dynpy_fft_length(int64_t n);
+
+/* Bytes of workspace that let `n_fft` transforms of length M be in flight in the two-pass
+ * split (0 for M <= 4096). */
+int64_t dynpy_fft_workspace_bytes(int64_t M, int64_t n_fft);
+
+/* ---- Wiener–Khinchin, batched ---------------------------------------------------------
+ * replaces  wiener_khinchin(f)  (qrax.py:147-156, ddrax.py:276-285, SRrax.py:216-225) applied
+ * per series by correlate() (qrax.py:158-166, ddrax.py:287-295, SRrax.py:226-230), summed
+ * over the series:   spectrum[k] += sum_s scale_s^2 |FFT_M(series_s)[k]|^2 .
+ *   re, im          series s starts at re + s*series_stride (im may be NULL: real series)
+ *   pack_real_pairs !=0 (im must be NULL): series 2t and 2t+1 share one complex transform
+ *   scale           optional per-series multiplier applied before the transform (NULL: 1)
+ *   spectrum        [M] accumulator (caller zeroes it), internal order
+ */
+int dynpy_wk_acf_sum_f64(const double* re, const double* im, int64_t n_series, int64_t n,
+                         int64_t series_stride, int pack_real_pairs, const double* scale,
+                         double* spectrum, int64_t M, void* ws, int64_t ws_bytes,
+                         dynpy_stream_t stream);
+
+/* acf[a][k] = scale * Re(FFT_M(spectrum_a))[k] , k < n_out  — the one inverse transform per
+ * output column that replaces np.fft.ifft(...)[:N].real/N of every series (qrax.py:154-155);
+ * pass scale = 1/(M*N) for the reference's biased estimator. */
+int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf, int64_t n_out,
+                       double scale, void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+
+/* ---- quadrupolar --------------------------------------------------------------------------
+ * replaces cart_to_spatial + groupby('label').apply(correlate)  (qrax.py:59-60,115-166):
+ * spectrum[3][M] accumulates, over the nuclei of this shard, the power spectra of
+ * R2,0 (acc 0), R2,+-1 (acc 1), R2,+-2 (acc 2). */
+int dynpy_qr_efg_to_spectrum_f64(const double* efg, int64_t n_nuclei, int64_t n_frames,
+                                 double* spectrum, int64_t M, void* ws, int64_t ws_bytes,
+                                 dynpy_stream_t stream);
+
+/* ---- dipolar --------------------------------------------------------------------------------
+ * np.mod(x, L) with numpy's sign convention (universe.py:296-308, distances.py:33-45). */
+int dynpy_wrap_f64(const double* x, double* out, int64_t n, double L, dynpy_stream_t stream);
+
+/* pdist_ortho (distances.py:155-242) for one frame, bit-exact: candidates visited in
+ * (aa,bb,cc) order, strict '<' from dmax^2, no FMA contraction, compacted in row-major
+ * upper-triangle order.  ux/uy/uz are read with element stride `stride`.
+ * Outputs have capacity n(n-1)/2; *count (device int64) receives the number of rows.
+ * ws: at least dynpy_pdist_workspace_bytes(n). */
+int64_t dynpy_pdist_workspace_bytes(int64_t n);
+int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, int64_t stride,
+                          int64_t n, double a, double b, double c, const int64_t* index,
+                          double dmax, double* dx, double* dy, double* dz, double* dr,
+                          int64_t* atom0, int64_t* atom1, int64_t* projection, int64_t* count,
+                          void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+
+/* frames in which each pair's minimum-image distance is < rmax  (the presence rule of
+ * compute_atom_two, DDparse.py:148): counts[p] in [0, n_frames]. coords are WRAPPED. */
+int dynpy_dd_pair_count_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                            const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
+                            double a, double b, double c, double rmax, int64_t* counts,
+                            dynpy_stream_t stream);
+
+/* Fused dipolar path for pairs present in every frame; replaces pdist_ortho per frame +
+ * cart_to_dipolar_from_df + groupby(pair).apply(correlate) + the pair sum
+ * (distances.py:131-145, ddrax.py:110-126,287-295, DDparse.py:81-104):
+ * spectrum[7][M] accumulates sum_pairs |FFT|^2 of Y20,Y21,Y22,(r^-3 - mean),F20,F21,F22
+ * (CSV column order of avg-acf.csv).  coords are WRAPPED, [n_atoms][3][n_frames].
+ * ws: dynpy_dd_workspace_bytes(n_frames, M, items) for `items` pair-pairs per batch (>=1). */
+int64_t dynpy_dd_workspace_bytes(int64_t n_frames, int64_t M, int64_t items);
+int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                                   const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
+                                   double a, double b, double c, double* spectrum, int64_t M,
+                                   void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+
+/* Ragged dipolar path (pairs absent from some frames, reference quirk B.3): every pair's
+ * series is the compressed sequence of its present frames, normalised by its own length,
+ * and lag k is binned at the k-th present frame:  G[7][n_frames] += ACF_p[k]/N_p at
+ * frame_of(p,k).  ws: dynpy_dd_ragged_workspace_bytes(n_frames, M, pairs_per_batch). */
+int64_t dynpy_dd_ragged_workspace_bytes(int64_t n_frames, int64_t M, int64_t pairs);
+int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                                     const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
+                                     double a, double b, double c, double rmax, double* G,
+                                     int64_t M, void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+
+/* ---- spin-rotation -------------------------------------------------------------------------
+ * replaces SR_func1 per (molecule, frame) (SRrax.py:438-510) and the backward-difference
+ * velocities (SRparse.py:127-134).  pos is RAW [n_atoms][3][n_frames]; vel may be NULL
+ * (v_t = (x_t - x_{t-1}) * inv_dt, outputs cover frames 1..n_frames-1) or explicit
+ * [n_atoms][3][n_frames] (outputs cover all frames).  mol_atoms[m][k]: atom indices of
+ * molecule m; mass[k] per atom of the molecule type; axis_atoms[m][4] = (a0,b0,a1,b1):
+ * d0 = minimum-image vector of atoms (a0,b0) as pdist_ortho would emit it, d1 of (a1,b1).
+ * J, omega: [n_mol][3][n_out]; axes: [n_mol][9][n_out] (xx,xy,xz,yx,...,zz); any may be NULL. */
+int dynpy_sr_angmom_f64(const double* pos, const double* vel, int64_t n_atoms, int64_t n_frames,
+                        const int32_t* mol_atoms, int64_t n_mol, int n_at_mol, const double* mass,
+                        const int32_t* axis_atoms, int axis_rule, double a, double b, double c,
+                        double inv_dt, double* J, double* omega, double* axes,
+                        dynpy_stream_t stream);
+
+/* ---- reductions -------------------------------------------------------------------------------
+ * scipy.integrate.simpson(y_col, x=x) for n_cols columns (qrax.py:193-195, ddrax.py:208-210,
+ * SRrax.py:576): y[col*col_stride + k], out[col]. */
+int dynpy_simpson_f64(const double* y, const double* x, int64_t n, int n_cols, int64_t col_stride,
+                      int mode, double* out, dynpy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNPY_B200_H */

@@ -1,0 +1,172 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle (oracle/oracle_np.py)
+and the committed reference vectors.  Run on the B200 box:  pytest -m gpu.
+
+Tolerances: ACF columns normwise max|dG|/max|G| <= 1e-9 (we assert much
+tighter where the arithmetic allows), pair lists bit-exact, rates <= 1e-8 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import oracle_np as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dynpy_b200 import ops as o
+    return o
+
+
+def dev(x, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).cuda()
+
+
+def nerr(got, ref):
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+# ------------------------------------------------------------------ engine: all plans
+@pytest.mark.parametrize("N", [1, 5, 16, 17, 33, 100, 316, 700, 1025, 2048,       # single pass M = 32 .. 4096
+                               2049, 5000, 9000, 20000, 40000, 70000, 100000,   # M1 = 2 .. 64
+                               150000, 300000, 600000])                          # M1 = 128 .. 512
+def test_wk_sum_complex_all_plans(ops, N):
+    rng = np.random.default_rng(N)
+    S = 3 if N > 20000 else 5
+    z = rng.normal(size=(S, N)) + 1j * rng.normal(size=(S, N))
+    z *= np.exp(-np.arange(N) / (0.3 * N + 1))[None]
+    spec = ops.wk_acf_sum(dev(z.real), dev(z.imag))
+    M = spec.numel()
+    assert M == max(32, 1 << int(np.ceil(np.log2(2 * N))))
+    acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
+    ref = sum(orc.wiener_khinchin(z[s]) for s in range(S))
+    assert nerr(acf, ref) < 1e-12, nerr(acf, ref)
+
+
+@pytest.mark.parametrize("N", [1 << 20, 3000000, 6000000])  # M1 = 512, 2048, 4096 (largest supported)
+def test_wk_sum_long_series(ops, N):
+    rng = np.random.default_rng(7)
+    z = rng.normal(size=(2, N))
+    spec = ops.wk_acf_sum(dev(z), pack_real_pairs=True)
+    M = spec.numel()
+    acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
+    ref = orc.wiener_khinchin(z[0]) + orc.wiener_khinchin(z[1])
+    assert nerr(acf, ref) < 1e-12
+
+
+@pytest.mark.parametrize("S,N", [(1, 50), (2, 50), (7, 333), (9, 5000), (3, 70000)])
+def test_wk_real_pair_packing_and_scale(ops, S, N):
+    rng = np.random.default_rng(S * 1000 + N)
+    x = rng.normal(size=(S, N)).cumsum(axis=1) / np.sqrt(N)
+    spec = ops.wk_acf_sum(dev(x), pack_real_pairs=True)
+    M = spec.numel()
+    acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
+    ref = sum(orc.wiener_khinchin(x[s]) for s in range(S))
+    assert nerr(acf, ref) < 1e-12
+    w = rng.uniform(0.5, 2.0, S)
+    spec = ops.wk_acf_sum(dev(x), scale=dev(w))
+    acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
+    ref = sum(w[s] ** 2 * orc.wiener_khinchin(x[s]) for s in range(S))
+    assert nerr(acf, ref) < 1e-12
+
+
+def test_wk_accumulates_and_matches_reference_vector(ops):
+    d = np.load(os.path.join(GOLDEN, "leaf_vectors.npz"))
+    z = d["wk_in"]
+    spec = ops.wk_acf_sum(dev(z.real[None]), dev(z.imag[None]))
+    spec = ops.wk_acf_sum(dev(z.real[None]), dev(z.imag[None]), spectrum=spec)  # second call accumulates
+    M, N = spec.numel(), len(z)
+    acf = ops.ifft_acf(spec, N, 0.5 / (M * N)).cpu().numpy()[0]
+    assert nerr(acf, d["wk_out"]) < 1e-13
+
+
+def test_argument_errors_are_loud(ops):
+    from dynpy_b200._lib import DynpyError
+    with pytest.raises(DynpyError):
+        ops.wk_acf_sum(torch.zeros((2, 8), dtype=torch.float64))  # CPU tensor: no CPU path
+    x = torch.zeros((2, 100), dtype=torch.float64, device="cuda")
+    with pytest.raises(DynpyError):
+        ops.wk_acf_sum(x, M=128)  # M < 2N-1
+    with pytest.raises(DynpyError):
+        ops.wk_acf_sum(x, M=384)  # not a power of two
+
+
+# ------------------------------------------------------------------ QR
+@pytest.mark.parametrize("S,N", [(1, 64), (2, 81), (5, 316), (4, 4096), (3, 70000)])
+def test_qr_spectrum(ops, S, N):
+    from dynpy_b200 import synth
+    efg = synth.efg_series(S, N, seed=S + N)
+    spec = ops.qr_efg_to_spectrum(efg.cuda())
+    M = spec.shape[1]
+    acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()
+    e = efg.numpy()
+    ref = np.zeros((5, N))
+    for s in range(S):
+        V = dict(Vxx=e[s, 0], Vyy=e[s, 1], Vzz=e[s, 2], Vxy=e[s, 3], Vxz=e[s, 4], Vyz=e[s, 5])
+        for m, r in enumerate(orc.qr_spatial(V)):
+            ref[m] += orc.wiener_khinchin(r)
+    for m, a in ((0, 2), (1, 1), (2, 0), (3, 1), (4, 2)):  # m = -2..2  <-  acc (R22, R21, R20)
+        assert nerr(acf[a], ref[m]) < 1e-12
+
+
+# ------------------------------------------------------------------ wrap + pdist (bit-exact)
+def test_wrap_bit_exact(ops):
+    rng = np.random.default_rng(3)
+    L = 30.651558
+    x = np.concatenate([rng.uniform(-3 * L, 3 * L, 5000), [0.0, -0.0, L, -L, -1e-18, 1e-18, 2 * L, -1e-300, 5e-324]])
+    got = ops.wrap(dev(x), L).cpu().numpy()
+    np.testing.assert_array_equal(got, np.mod(x, L))
+    assert got.max() <= L
+
+
+def test_pdist_reference_vectors(ops):
+    d = np.load(os.path.join(GOLDEN, "leaf_vectors.npz"))
+    for k in range(4):
+        x, y, z = d["pd%d_in" % k]
+        L, dmax = d["pd%d_par" % k]
+        got = ops.pdist_ortho(dev(x), dev(y), dev(z), L, L, L, dev(d["pd%d_idx" % k], torch.int64), dmax)
+        for c, nm in enumerate(("dx", "dy", "dz", "dr", "a0", "a1", "prj")):
+            np.testing.assert_array_equal(got[c].cpu().numpy(), d["pd%d_%s" % (k, nm)], err_msg="%d %s" % (k, nm))
+
+
+@pytest.mark.parametrize("n,dmax", [(0, 3.0), (1, 3.0), (2, 3.0), (2, 0.01), (300, 4.0), (768, 15.0), (1000, 1e9)])
+def test_pdist_vs_oracle(ops, n, dmax):
+    rng = np.random.default_rng(n)
+    a, b, c = 17.3, 19.1, 23.7
+    x, y, z = rng.uniform(0, a, n), rng.uniform(0, b, n), rng.uniform(0, c, n)
+    idx = np.arange(n, dtype=np.int64) * 3 + 7
+    got = ops.pdist_ortho(dev(x), dev(y), dev(z), a, b, c, dev(idx, torch.int64), dmax)
+    ref = orc.pdist_ortho(x, y, z, a, b, c, idx, dmax) if n >= 2 else [np.zeros(0)] * 7
+    for k in range(7):
+        np.testing.assert_array_equal(got[k].cpu().numpy(), ref[k])
+
+
+def test_pdist_strided_frame_layout(ops):
+    rng = np.random.default_rng(9)
+    A, F, L = 40, 6, 11.0
+    X = rng.uniform(0, L, (A, 3, F))
+    Xd = dev(X)
+    f = 4
+    got = ops.pdist_ortho(Xd[:, 0, f], Xd[:, 1, f], Xd[:, 2, f], L, L, L, dev(np.arange(A), torch.int64), 5.0,
+                          stride=3 * F)
+    ref = orc.pdist_ortho(X[:, 0, f], X[:, 1, f], X[:, 2, f], L, L, L, np.arange(A), 5.0)
+    for k in range(7):
+        np.testing.assert_array_equal(got[k].cpu().numpy(), ref[k])
+
+
+# ------------------------------------------------------------------ Simpson
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 10, 11, 316, 317, 100000, 100001])
+@pytest.mark.parametrize("mode", ["cartwright", "avg"])
+def test_simpson(ops, n, mode):
+    rng = np.random.default_rng(n)
+    x = np.cumsum(rng.uniform(0.5, 1.5, n)) if n < 1000 else np.arange(n) * 0.001
+    y = rng.normal(size=(3, n)) + np.exp(-np.arange(n) / (0.2 * n + 1))
+    got = ops.simpson(dev(y), dev(x), mode).cpu().numpy()
+    ref = np.array([orc.simpson(y[c], x, mode) for c in range(3)])
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-13)
