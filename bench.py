@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the dipolar G(tau)+R1 hot path (BASELINE.json metric: pair-frames/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+One "step" = one pass of the hot path over the whole workload: wrapped coordinates resident in
+HBM -> pair vectors -> Y2m r^-3 words -> batched FFTs -> accumulated spectra -> summed ACFs
+G(tau) (7 columns) -> Simpson J(0) -> 1/T1.  Under torchrun every rank holds the (replicated)
+coordinates, transforms a contiguous shard of the pairs and the spectra-derived ACFs are
+all-reduced once (NCCL); the timed region is bracketed by barrier + synchronize and the
+reported time is the max over ranks.
+
+Workloads: cfg2 (default) 256 H2O x 1e5 frames, all 130 816 H-H pairs, gapless
+rmax; cfg5 512 H2O x 1e6 frames, 523 264 intermolecular H-H pairs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_PAIR_FRAME = 48.0  # two fp64 xyz triplets per pair-frame
+
+WORKLOADS = {
+    "cfg2": dict(nmol=256, frames=100_000, pair_type="all", seed=2,
+                 name="cfg2: dipolar, 256 H2O x 1e5 frames, all H-H pairs, gapless rmax"),
+    "cfg5": dict(nmol=512, frames=1_000_000, pair_type="inter", seed=5,
+                 name="cfg5: dipolar, 512 H2O x 1e6 frames, intermolecular H-H pairs, gapless rmax"),
+    "small": dict(nmol=32, frames=20_000, pair_type="all", seed=2,
+                  name="small: dipolar, 32 H2O x 2e4 frames, all H-H pairs, gapless rmax"),
+}
+
+
+def h_pairs(nmol, pair_type):
+    """H-only atom indexing: H atoms 2m, 2m+1 belong to molecule m; pairs i<j."""
+    nh = 2 * nmol
+    i, j = np.triu_indices(nh, k=1)
+    if pair_type == "inter":
+        keep = (i // 2) != (j // 2)
+        i, j = i[keep], j[keep]
+    elif pair_type == "intra":
+        keep = (i // 2) == (j // 2)
+        i, j = i[keep], j[keep]
+    return i.astype(np.int32), j.astype(np.int32)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.path = "/tmp/dynpy_clocks_%d.csv" % os.getpid()
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap,power.draw"
+        try:
+            self.fh = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.fh,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                t = [x.strip() for x in ln.split(",")]
+                if len(t) < 7:
+                    continue
+                sm.append(float(t[0])); mx.append(float(t[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    from oracle import oracle_np as orc
+    w, pairs, L = args
+    return orc.dd_pairs_gapless(w, pairs, L)
+
+
+def reference_arm(args, wl):
+    """The reference's algorithm (oracle port: per-pair min-image vectors, angle-form Y2m, one
+    zero-padded fft/ifft per series as in wiener_khinchin) on the host cores, one process per core
+    over disjoint pair shards, on a bounded sample of the workload's pairs."""
+    import multiprocessing as mp
+
+    import torch
+
+    from dynpy_b200 import synth
+    from oracle import oracle_np as orc  # noqa: F401
+    cores = os.cpu_count() or 1
+    F = wl["frames"] if wl["frames"] <= 100_000 else 100_000
+    nh_sample = 16
+    box = synth.water_box(wl["nmol"], seed=wl["seed"])
+    hmask = torch.tensor([s == "H" for s in box.symbols])
+    traj = box.trajectory(F, atom_mask=hmask.nonzero()[:, 0][:nh_sample]).numpy()
+    L = box.celldm
+    w = np.mod(traj, L)
+    pi, pj = h_pairs(nh_sample // 2, wl["pair_type"])
+    per_step = min(len(pi), max(cores * 2, 8))
+    shards = [list(zip(pi[k:per_step:cores].tolist(), pj[k:per_step:cores].tolist())) for k in range(cores)]
+    shards = [s for s in shards if s]
+    times = []
+    with mp.get_context("fork").Pool(len(shards)) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            parts = pool.map(_ref_worker, [(w, s, L) for s in shards])
+            G = sum(parts)
+            t = np.arange(F) * 0.001
+            orc.dd_rates(t, G[4] * 2 / nh_sample, G[5] * 2 / nh_sample, G[6] * 2 / nh_sample)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = per_step * F / (ms * 1e-3)
+    sample = "%d pairs x %d frames per step (of %s)" % (per_step, F, wl["name"])
+    line = {"impl": "reference", "metric": "pair-frames/s (dipolar G(tau)+R1)", "value": value, "unit": "pair-frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pair-frames/s", "cores": len(shards), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "pair-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(box, wl, F, budget_s=20.0):
+    """Single-core oracle port on a bounded sample (a few pairs x all frames)."""
+    import torch
+
+    from oracle import oracle_np as orc
+    F = min(F, 100_000)
+    nh = 8
+    hmask = torch.tensor([s == "H" for s in box.symbols])
+    traj = box.trajectory(F, atom_mask=hmask.nonzero()[:, 0][:nh].to(box.lattice.device)).cpu().numpy()
+    w = np.mod(traj, box.celldm)
+    pi, pj = h_pairs(nh // 2, "all")
+    pairs = list(zip(pi.tolist(), pj.tolist()))
+    t0 = time.perf_counter()
+    done = 0
+    for p in pairs:
+        orc.dd_pairs_gapless(w, [p], box.celldm)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done * F / dt, "unit": "pair-frames/s", "cores": 1, "kind": "port",
+            "sample": "%d pairs x %d frames of the workload, numpy restatement of the reference path, 1 core" % (done, F)}
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def native_arm(args, wl):
+    import torch
+    import torch.distributed as tdist
+
+    from dynpy_b200 import _lib, ddrax, dist, ops, synth
+    rank, world, local = dist.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    F = wl["frames"] if args.frames is None else args.frames
+    box = synth.water_box(wl["nmol"], seed=wl["seed"]).to(dev)
+    hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device=dev)
+    raw = box.trajectory(F, chunk=2048, atom_mask=hidx)          # [2*nmol, 3, F] raw bohr, resident
+    L = box.celldm
+    cell = (L, L, L)
+    rmax = L                                                       # > sqrt(3)/2 L: every pair in every frame
+    pi_h, pj_h = h_pairs(wl["nmol"], wl["pair_type"])
+    if args.pairs:
+        pi_h, pj_h = pi_h[:args.pairs], pj_h[:args.pairs]
+    P = len(pi_h)
+    pi, pj = torch.from_numpy(pi_h).to(dev), torch.from_numpy(pj_h).to(dev)
+    wrapped = torch.empty_like(raw)
+    tdev = torch.arange(1, F + 1, device=dev, dtype=torch.float64) * 0.001
+    M = ops.fft_length(F)
+    lo, hi = dist.shard_range(P, rank, world)
+    ws_budget = int(args.ws_gb * (1 << 30))
+
+    def step(src):
+        ops.wrap(src, L, out=wrapped)
+        # pair_acf_sum with an explicit workspace budget
+        G = torch.zeros((7, F), dtype=torch.float64, device=dev)
+        if hi > lo:
+            spec = ops.dd_pairs_to_spectrum(wrapped, pi[lo:hi], pj[lo:hi], cell, M=M, ws_budget=ws_budget)
+            G += ops.ifft_acf(spec, F, 1.0 / (float(M) * float(F)))
+        dist.allreduce_sum_(G)
+        G *= 2.0 / (2 * wl["nmol"])
+        EN = ddrax.spec_dens_extr_narr(tdev, G, "cartwright")     # Simpson on the device, 6 doubles to host
+        return G, ddrax.dipolar(EN, "1H", "1H")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        e1.synchronize()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        return float(ms.item()) / steps, out
+
+    for _ in range(args.warmup):
+        step(raw)
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.dynpy_profile_enable(1)
+    lib.dynpy_profile_read(None, None)
+    ms_step, (G, (rate, tc, F0)) = timed(lambda: step(raw), args.steps)
+    import ctypes as C
+    prof_ms = (C.c_double * 4)()
+    prof_n = (C.c_int64 * 4)()
+    lib.dynpy_profile_read(prof_ms, prof_n)
+    lib.dynpy_profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public API with HOST buffers (H2D of the raw coordinates and
+    #      D2H of G(tau) inside the timed region)
+    host_raw = torch.empty(raw.shape, dtype=torch.float64, pin_memory=True)
+    host_raw.copy_(raw)
+    host_G = torch.empty((7, F), dtype=torch.float64, pin_memory=True)
+    staging = torch.empty_like(raw)
+
+    def e2e_step():
+        staging.copy_(host_raw, non_blocking=True)
+        Gd, r = step(staging)
+        host_G.copy_(Gd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return Gd, r
+
+    e2e_step()
+    ms_e2e, _ = timed(e2e_step, max(1, min(args.steps, 3)))
+
+    if rank != 0:
+        return
+    hbm, how = peaks()
+    pf_total = float(P) * float(F)
+    value = pf_total / (ms_step * 1e-3)
+    names = ["dd_words", "fft_cols", "fft_rows", "other"]
+    per = {names[k]: {"ms_per_step": prof_ms[k] / args.steps, "launches_per_step": prof_n[k] / args.steps}
+           for k in range(4)}
+    dom = max(range(3), key=lambda k: prof_ms[k])
+    pf_rank = float(hi - lo) * float(F)
+    t_dom = prof_ms[dom] / args.steps * 1e-3
+    achieved = ALG_BYTES_PER_PAIR_FRAME * pf_rank / t_dom / 1e9 if t_dom > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(names[dom])
+    except Exception:
+        pass
+    line = {
+        "metric": "pair-frames/s (dipolar G(tau)+R1)", "value": value, "unit": "pair-frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "pairs": P, "frames": F, "fft_length": M, "cell_bohr": L,
+                   "l2": "inputs larger than L2 (coords %.2f GB, per-batch FFT intermediates > 126 MB); no flush" %
+                         (raw.numel() * 8 / 1e9),
+                   "sharding": "contiguous pair blocks per rank, one NCCL all-reduce of G[7,F]" if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": pf_total / (ms_e2e * 1e-3), "unit": "pair-frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(raw.numel() * 8), "d2h_bytes_per_step": int(7 * F * 8 + 48)},
+        "gpu_launches": int(sum(prof_n)) + 2 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                     "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
+                     "algorithmic_bytes_per_pair_frame": ALG_BYTES_PER_PAIR_FRAME,
+                     "kernel_share_of_step": prof_ms[dom] / args.steps / ms_step,
+                     "whole_step_frac": ALG_BYTES_PER_PAIR_FRAME * pf_rank / (ms_step * 1e-3) / 1e9 / hbm,
+                     "per_kernel": per},
+        "result": {"rate_1_over_T1_per_nH": rate, "tau_c_ps": tc, "G20_0": float(G[4, 0])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(box, wl, F)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=None, help="override the frame count (debug)")
+    ap.add_argument("--pairs", type=int, default=None, help="use only the first PAIRS pairs (debug)")
+    ap.add_argument("--ws-gb", type=float, default=4.0, help="workspace budget of the fused dipolar call")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        reference_arm(args, wl)
+    else:
+        native_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

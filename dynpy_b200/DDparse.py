@@ -1,0 +1,100 @@
+"""Dipolar driver — mirror of the reference's DDparse.py (DD_module_main :17-132,
+prep_DD_uni1 :133-169) on top of the CUDA path.  Same parameter classes, prompts, stdout
+result lines and CSV files (``<traj_dir><traj>/avg-acf.csv``, ``<traj_dir>DD-results.csv``)."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import ddrax, dist, ops, parseMD, topology
+from .config import default_simpson_mode
+from .helper import which_trajs
+
+
+def select_pairs(symbols, topo, nat_per_mol, pair_type, analyte_label):
+    """Pair rows the reference keeps (DDparse.py:53-60): H–H (or analyte_label–H) with
+    label0 < label1, intra / inter / all by molecule membership.  Returns int32 arrays."""
+    A = len(symbols)
+    sym = np.array(symbols)
+    i, j = np.triu_indices(A, k=1)
+    if analyte_label:  # label 0 is falsy in the reference as well (DDparse.py:53)
+        mai = np.arange(A) % nat_per_mol
+        sel = (mai[i] == analyte_label) & (sym[j] == 'H')
+    else:
+        sel = (sym[i] == 'H') & (sym[j] == 'H')
+    m = topo.mol_rank
+    if pair_type == 'intra':
+        sel &= m[i] == m[j]
+    elif pair_type == 'inter':
+        sel &= m[i] != m[j]
+    return i[sel].astype(np.int32), j[sel].astype(np.int32)
+
+
+def dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson_mode):
+    """One trajectory -> (acf_avg DataFrame, rate, tau_c, F0, info)."""
+    try:
+        dmax = DD.rmax
+    except AttributeError:
+        dmax = 15
+    cell = (float(PD.celldm),) * 3
+    wrapped = ops.wrap(tr.pos, cell[0])
+    topo, _ = topology.build_topology(wrapped, tr.symbols, cell, dmax, bond_extra=0.45)
+    topo.classify_exact(DD.identifier)  # raises like Molecule.classify when the formula is absent
+    nat_per_mol = topology.atoms_per_formula(DD.identifier)
+    pi, pj = select_pairs(tr.symbols, topo, nat_per_mol, pair_type, analyte_label)
+    dev = wrapped.device
+    G, hit, n_spins, info = ddrax.pair_acf_sum(wrapped, torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev),
+                                               cell, dmax)
+    if n_spins == 0:
+        raise ValueError("no pair of the requested kind is ever inside rmax=%r" % (dmax,))
+    G = (G[:, hit] * (2.0 / n_spins)).contiguous()
+    tdev = (torch.from_numpy(tr.frames).to(dev)[hit].to(torch.float64) * float(PD.timestep)).contiguous()
+    EN = ddrax.spec_dens_extr_narr(tdev, G, simpson_mode)
+    rax, tc, F = ddrax.dipolar(EN, symbol1=analyte_species, symbol2='1H')
+    acf_avg = pd.DataFrame({'time': tdev.cpu().numpy()})
+    Gh = G.cpu().numpy()
+    for c, name in enumerate(ddrax.G_COLUMNS):
+        acf_avg[name] = Gh[c]
+    return acf_avg, rax, tc, F, info
+
+
+def DD_module_main(PD, DD):
+    outer_start_time = time.time()
+    analyte_label = getattr(DD, 'analyte_label', None)
+    analyte_species = getattr(DD, 'analyte_species', '1H')
+    try:
+        pair_type = DD.pair_type
+        if pair_type.casefold() not in ['intra', 'inter', 'all']:
+            pair_type = 'all'
+            print("Inter- and intramolecular pairs will be considered.\n")
+    except AttributeError:
+        pair_type = 'all'
+    simpson_mode = getattr(DD, 'simpson_mode', None) or default_simpson_mode()
+    rank, world = dist.rank_world()
+    if rank == 0:
+        which_trajs(PD)
+    dist.barrier()
+    res = {}
+    for t, traj in enumerate(PD.trajs):
+        inner_start_time = time.time()
+        tr = parseMD.PARSE_MD(PD, traj)
+        print("computing two-atom distances...")
+        print("computing dipolar quantities...")
+        print("computing TCFs...")
+        acf_avg, rax, tc, F, info = dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson_mode)
+        torch.cuda.synchronize()
+        print("--- {t:.2f} seconds ---".format(t=time.time() - inner_start_time))
+        if rank == 0:
+            acf_avg.to_csv(PD.traj_dir + traj + '/avg-acf.csv')
+        print("1/T1/nH = {r:.3e} Hz, tau_c = {t:.3e} ps, <F(0)^2> = {f:.3e} au^-6".format(r=rax, t=tc, f=F))
+        print("For intramolecular contrib. in heteronuclear systems (e.g. C--H relaxation of 13C), multiply 1/T1/nH "
+              "by number of bonded spins to obtain 1/T1. E.g. for C-13 in methyl group, nH=3")
+        res[traj] = [rax, tc, F]
+    res_df = pd.DataFrame(res).T
+    res_df.columns = ["1/T1/nH", "tau_c", "<F(0)^2>"]
+    if rank == 0:
+        res_df.to_csv(PD.traj_dir + 'DD-results.csv')
+    return res_df

@@ -22,15 +22,20 @@ SIGNATURES = {
     "dynpy_version": (i32, []),
     "dynpy_last_error": (C.c_char_p, []),
     "dynpy_device_sm_count": (i32, []),
+    "dynpy_profile_enable": (i32, [i32]),
+    "dynpy_profile_read": (i32, [p, p]),
     "dynpy_fft_length": (i64, [i64]),
     "dynpy_fft_workspace_bytes": (i64, [i64, i64]),
     "dynpy_wk_acf_sum_f64": (i32, [p, p, i64, i64, i64, i32, p, p, i64, p, i64, p]),
     "dynpy_ifft_acf_f64": (i32, [p, i32, i64, p, i64, f64, p, i64, p]),
+    "dynpy_wk_each_workspace_bytes": (i64, [i64, i64]),
+    "dynpy_wk_acf_each_f64": (i32, [p, p, i64, i64, i64, p, i64, p, i64, p]),
     "dynpy_qr_efg_to_spectrum_f64": (i32, [p, i64, i64, p, i64, p, i64, p]),
     "dynpy_wrap_f64": (i32, [p, p, i64, f64, p]),
     "dynpy_pdist_workspace_bytes": (i64, [i64]),
     "dynpy_pdist_ortho_f64": (i32, [p, p, p, i64, i64, f64, f64, f64, p, f64, p, p, p, p, p, p, p, p, p, i64, p]),
-    "dynpy_dd_pair_count_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, p]),
+    "dynpy_topology_check_f64": (i32, [p, i64, i64, p, f64, p, f64, f64, f64, f64, p, p]),
+    "dynpy_dd_pair_count_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, p, p]),
     "dynpy_dd_workspace_bytes": (i64, [i64, i64, i64]),
     "dynpy_dd_pairs_to_spectrum_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, p, i64, p, i64, p]),
     "dynpy_dd_ragged_workspace_bytes": (i64, [i64, i64, i64]),

@@ -2,6 +2,8 @@
 // batch loops.  All compute is in the kernels of fft_engine.cuh / kernels_misc.cu.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "../../include/dynpy_b200.h"
 #include "kernels.h"
 
@@ -22,6 +24,32 @@ int fail_cuda(cudaError_t e, const char* where) {
 }
 
 static DeviceState g_dev[64];
+
+// ---- profiling hooks -------------------------------------------------------------------
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[PROF_NCLS];  // begin/end pairs
+    std::vector<cudaEvent_t> pool;
+};
+static ProfState g_prof;
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof.pool.empty()) { e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof.on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_prof.ev[cls].push_back(e);
+}
+void prof_end(int cls, cudaStream_t st) {
+    if (!g_prof.on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_prof.ev[cls].push_back(e);
+}
 
 int get_device_state(DeviceState** out, cudaStream_t st) {
     int dev = -1;
@@ -77,6 +105,32 @@ int dynpy_device_sm_count(void) {
     DeviceState* d;
     int rc = get_device_state(&d, 0);
     return rc ? rc : d->n_sm;
+}
+
+int dynpy_profile_enable(int on) {
+    g_prof.on = on != 0;
+    return DYNPY_OK;
+}
+
+// Sum of device time (ms) and number of launches per kernel class since the last read;
+// synchronises the device.  ms[4], launches[4]: words, cols, rows, other.
+int dynpy_profile_read(double* ms_host, int64_t* launches_host) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail_cuda(e, "profile sync");
+    for (int c = 0; c < PROF_NCLS; ++c) {
+        double tot = 0.0;
+        auto& v = g_prof.ev[c];
+        for (size_t k = 0; k + 1 < v.size(); k += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, v[k], v[k + 1]);
+            tot += t;
+        }
+        if (ms_host) ms_host[c] = tot;
+        if (launches_host) launches_host[c] = (int64_t)(v.size() / 2);
+        for (auto ev : v) g_prof.pool.push_back(ev);
+        v.clear();
+    }
+    return DYNPY_OK;
 }
 
 int64_t dynpy_fft_length(int64_t n) {
@@ -174,6 +228,72 @@ int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf
     return DYNPY_OK;
 }
 
+int64_t dynpy_wk_each_workspace_bytes(int64_t M, int64_t n_series) {
+    if (n_series < 1) n_series = 1;
+    i64 t = M > DYNPY_ROW_LEN ? (n_series < 16 ? n_series : 16) * M * (i64)sizeof(cd) : 0;
+    return n_series * align_up(M * 8, 256) + t + 512;
+}
+
+int dynpy_wk_acf_each_f64(const double* re, const double* im, int64_t n_series, int64_t n, int64_t series_stride,
+                          double* acf, int64_t M, void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_M(M, n);
+    if (rc) return rc;
+    if (n_series < 0 || !re || !acf || series_stride < n || !ws) {
+        set_error("dynpy_wk_acf_each_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    if (n_series == 0) return DYNPY_OK;
+    DeviceState* d;
+    rc = get_device_state(&d, st);
+    if (rc) return rc;
+    // carve: T (up to 16 transforms) | P[cap][M]
+    const bool two = M > DYNPY_ROW_LEN;
+    i64 cap = n_series;
+    while (cap > 1 && dynpy_wk_each_workspace_bytes(M, cap) > ws_bytes) cap = (cap + 1) / 2;
+    if (dynpy_wk_each_workspace_bytes(M, cap) > ws_bytes) {
+        set_error("dynpy_wk_acf_each_f64: workspace too small (need >= %lld bytes)",
+                  (long long)dynpy_wk_each_workspace_bytes(M, 1));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    const i64 T_cap = two ? (cap < 16 ? cap : 16) : 0;
+    cd* T = two ? (cd*)ws : nullptr;
+    double* P = (double*)((char*)ws + align_up(T_cap * M * (i64)sizeof(cd), 256));
+    const i64 pstride = align_up(M * 8, 256) / 8;
+    if (pstride != M) { set_error("internal: unaligned spectrum stride"); return DYNPY_ERR_INVALID; }
+    for (i64 s0 = 0; s0 < n_series; s0 += cap) {
+        const i64 cnt = n_series - s0 < cap ? n_series - s0 : cap;
+        PlanarLoader ld;
+        memset(&ld, 0, sizeof(ld));
+        ld.re = re + s0 * series_stride;
+        ld.im = im ? im + s0 * series_stride : nullptr;
+        ld.hi = series_stride;
+        ld.nslots = 1;
+        ld.N = n;
+        ld.n_im_valid = cnt;
+        ld.bias_slot = -1;
+        EpiParams ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.out = P;
+        ep.M = M;
+        ep.nslots = 1;
+        DYNPY_CHECK(forward_planar_power(ld, ep, cnt, M, 1, T, T_cap, d->tw4096, d->n_sm, st), "wk each forward");
+        SpectrumLoader sl;
+        sl.S = P;
+        sl.M = M;
+        sl.M1 = two ? (int)(M / DYNPY_ROW_LEN) : 1;
+        EpiParams e2;
+        memset(&e2, 0, sizeof(e2));
+        e2.out = acf + s0 * n;
+        e2.M = M;
+        e2.nslots = 1;
+        e2.n_out = n;
+        e2.scale = 1.0 / ((double)M * (double)n);
+        DYNPY_CHECK(forward_spectrum_real(sl, e2, cnt, M, 1, T, T_cap, d->tw4096, d->n_sm, st), "wk each inverse");
+    }
+    return DYNPY_OK;
+}
+
 // ------------------------------------------------------------------------------------------ QR
 int dynpy_qr_efg_to_spectrum_f64(const double* efg, int64_t n_nuclei, int64_t n_frames, double* spectrum, int64_t M,
                                  void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
@@ -254,7 +374,7 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
 
 int dynpy_dd_pair_count_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
                             const int32_t* pair_j, int64_t n_pairs, double a, double b, double c, double rmax,
-                            int64_t* counts, dynpy_stream_t stream) {
+                            int64_t* counts, int32_t* frame_hit, dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!coords || !pair_i || !pair_j || !counts || n_frames < 1 || n_pairs < 0 || n_atoms < 1) {
         set_error("dynpy_dd_pair_count_f64: invalid arguments");
@@ -266,8 +386,26 @@ int dynpy_dd_pair_count_f64(const double* coords, int64_t n_atoms, int64_t n_fra
     for (i64 p0 = 0; p0 < n_pairs; p0 += (i64)1 << 30) {
         i64 cnt = n_pairs - p0 < ((i64)1 << 30) ? n_pairs - p0 : ((i64)1 << 30);
         DYNPY_CHECK(launch_dd_pair_count(coords, n_frames, pair_i + p0, pair_j + p0, cnt, a, b, c, rmax,
-                                         (i64*)counts + p0, st), "dd pair count");
+                                         (i64*)counts + p0, frame_hit, st), "dd pair count");
     }
+    return DYNPY_OK;
+}
+
+int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const double* rcov,
+                             double bond_extra, const uint8_t* expect, double a, double b, double c, double dmax,
+                             uint64_t* out, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!coords || !rcov || !expect || !out || n_atoms < 1 || n_frames < 1 || n_atoms > 65535) {
+        set_error("dynpy_topology_check_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    const unsigned long long init[2] = {0ull, ~0ull};
+    DYNPY_CHECK(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st), "topology init");
+    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
+                                      (unsigned long long*)out, st), "topology check");
     return DYNPY_OK;
 }
 
@@ -322,8 +460,11 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
 
     for (i64 it0 = 0; it0 < items; it0 += cap) {
         const i64 cnt = items - it0 < cap ? items - it0 : cap;
-        DYNPY_CHECK(launch_dd_words(coords, n_atoms, N, pair_i, pair_j, 2 * it0, n_pairs, cnt, a, b, c, Z, bias, st),
-                    "dd words");
+        {
+            ProfScope prof(PROF_WORDS, st);
+            DYNPY_CHECK(launch_dd_words(coords, n_atoms, N, pair_i, pair_j, 2 * it0, n_pairs, cnt, a, b, c, Z, bias, st),
+                        "dd words");
+        }
         PlanarLoader ld;
         memset(&ld, 0, sizeof(ld));
         ld.re = Z;

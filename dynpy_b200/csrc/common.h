@@ -21,6 +21,17 @@ struct DeviceState {
 // Per-device state for the current device (allocates + fills the twiddle table on first use).
 int get_device_state(DeviceState** out, cudaStream_t st);
 
+// Optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py for
+// the live roofline numbers.  Classes: 0 dipolar word generator, 1 column pass, 2 row pass, 3 other.
+enum ProfClass { PROF_WORDS = 0, PROF_COLS = 1, PROF_ROWS = 2, PROF_OTHER = 3, PROF_NCLS = 4 };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+    int cls; cudaStream_t st;
+    ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(cls, st); }
+    ~ProfScope() { prof_end(cls, st); }
+};
+
 #define DYNPY_CHECK(call, where)                                   \
     do {                                                           \
         cudaError_t _e = (call);                                   \

@@ -17,6 +17,7 @@ static cudaError_t launch_rows_L(const Loader& ld, const EpiParams& ep, const cd
         if (e != cudaSuccess) return e;
     }
     dim3 grid(TWO_PASS ? M1 : 1, gy);
+    ProfScope prof(PROF_ROWS, st);
     kern<<<grid, NT, smem, st>>>(ld, ep, tw, f0, f1, gy, M1);
     return cudaGetLastError();
 }
@@ -48,6 +49,7 @@ static cudaError_t launch_cols_M1(const Loader& ld, cd* T, const cd* tw, i64 M, 
         if (e != cudaSuccess) return e;
     }
     dim3 grid(DYNPY_ROW_LEN / C, gy);
+    ProfScope prof(PROF_COLS, st);
     kern<<<grid, NT, smem, st>>>(ld, T, tw, M, 1.0 / (double)M, f0, f1, gy);
     return cudaGetLastError();
 }

@@ -21,7 +21,10 @@ cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i
 cudaError_t launch_dd_words(const double* X, i64 A, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs,
                             i64 items, double a, double b, double c, double* Z, double* bias, cudaStream_t st);
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
-                                 double b, double c, double rmax, i64* counts, cudaStream_t st);
+                                 double b, double c, double rmax, i64* counts, int* frame_hit, cudaStream_t st);
+cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
+                                  const unsigned char* expect, double a, double b, double c, double dmax,
+                                  unsigned long long* out, cudaStream_t st);
 cudaError_t launch_dd_ragged_words(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 npairs,
                                    double a, double b, double c, double rmax, double* W, int* fidx, i64* lens,
                                    double* scale, double* bias, cudaStream_t st);

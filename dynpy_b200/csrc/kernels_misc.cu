@@ -297,7 +297,7 @@ cudaError_t launch_dd_words(const double* X, i64 A, i64 N, const int* pi, const 
 // frames with r2 < rmax^2 per pair: one CTA per pair
 __global__ void __launch_bounds__(256)
 k_dd_pair_count(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
-                double a, double b, double c, double rmax2, i64* __restrict__ counts) {
+                double a, double b, double c, double rmax2, i64* __restrict__ counts, int* __restrict__ frame_hit) {
     __shared__ double sh[8];
     const i64 p = blockIdx.x;
     const double* xi = X + (i64)pi[p] * 3 * N;
@@ -308,15 +308,57 @@ k_dd_pair_count(const double* __restrict__ X, i64 N, const int* __restrict__ pi,
         axis_min(__ldg(xi + n), __ldg(xj + n), a, d, sx);
         axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, d, sy);
         axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, d, sz);
-        if (__dadd_rn(__dadd_rn(sx, sy), sz) < rmax2) cnt += 1.0;
+        if (__dadd_rn(__dadd_rn(sx, sy), sz) < rmax2) {
+            cnt += 1.0;
+            if (frame_hit) frame_hit[n] = 1;  // every writer stores the same value
+        }
     }
     const double t = block_sum_256(cnt, sh);
     if (threadIdx.x == 0) counts[p] = (i64)t;
 }
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
-                                 double b, double c, double rmax, i64* counts, cudaStream_t st) {
+                                 double b, double c, double rmax, i64* counts, int* frame_hit, cudaStream_t st) {
     if (n_pairs <= 0) return cudaSuccess;
-    k_dd_pair_count<<<(unsigned)n_pairs, 256, 0, st>>>(X, N, pi, pj, a, b, c, rmax * rmax, counts);
+    k_dd_pair_count<<<(unsigned)n_pairs, 256, 0, st>>>(X, N, pi, pj, a, b, c, rmax * rmax, counts, frame_hit);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ static-topology check
+// For every frame and every atom pair i<j: is (min-image dr <= rcov_i + rcov_j + extra) equal to
+// the bond flag of the reference frame?  (The reference re-detects bonds/molecules in every
+// frame, distances.py:244-257 + universe.py:411-451; the CUDA path indexes molecules once and
+// verifies here that this is equivalent.)  out[0] = number of mismatching pair-frames,
+// out[1] = first frame with a mismatch.
+__global__ void __launch_bounds__(256)
+k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
+                 const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
+                 unsigned long long* __restrict__ out) {
+    const i64 n = (i64)blockIdx.x * 256 + threadIdx.x;
+    const i64 i = blockIdx.y;
+    if (n >= N) return;
+    const double xi = X[(i * 3 + 0) * N + n], yi = X[(i * 3 + 1) * N + n], zi = X[(i * 3 + 2) * N + n];
+    const double ri = rcov[i];
+    unsigned long long bad = 0;
+    for (i64 j = i + 1; j < A; ++j) {
+        double d, sx, sy, sz;
+        axis_min(xi, __ldg(X + (j * 3 + 0) * N + n), a, d, sx);
+        axis_min(yi, __ldg(X + (j * 3 + 1) * N + n), b, d, sy);
+        axis_min(zi, __ldg(X + (j * 3 + 2) * N + n), c, d, sz);
+        const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+        const bool bond = (r2 < dmax2) && (sqrt(r2) <= __dadd_rn(__dadd_rn(ri, rcov[j]), extra));
+        if (bond != (expect[i * A + j] != 0)) ++bad;
+    }
+    if (bad) {
+        atomicAdd(out, bad);
+        atomicMin(out + 1, (unsigned long long)n);
+    }
+}
+cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
+                                  const unsigned char* expect, double a, double b, double c, double dmax,
+                                  unsigned long long* out, cudaStream_t st) {
+    if (A < 2 || N < 1) return cudaSuccess;
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)(A - 1));
+    k_topology_check<<<grid, 256, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax, out);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,113 @@
+"""Dipolar numerics — host-side mirror of the live part of the reference's ddrax.py.
+
+``pair_acf_sum`` replaces pdist_ortho-per-frame + cart_to_dipolar_from_df +
+groupby(['label0','label1']).apply(correlate) + the sum over pairs
+(distances.py:131-145, ddrax.py:110-126,287-295, DDparse.py:81-104) with CUDA kernels;
+``spec_dens_extr_narr`` and ``dipolar`` keep the reference's names and formulas
+(ddrax.py:186-274)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import dist, ops
+from .nuc import HBAR, MU_0, nuc
+
+G_COLUMNS = ['$G_{Y2,0}$', '$G_{Y2,1}$', '$G_{Y2,2}$', '$G_{r}$', '$G_{2,0}$', '$G_{2,1}$', '$G_{2,2}$']
+
+
+def gapless(cell, rmax) -> bool:
+    """True when every pair is inside rmax in every frame: min-image distance <= sqrt(a^2+b^2+c^2)/2."""
+    half_diag2 = 0.25 * (cell[0] ** 2 + cell[1] ** 2 + cell[2] ** 2)
+    return float(rmax) ** 2 > half_diag2 * (1.0 + 1e-9)
+
+
+def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True):
+    """Sum over pairs of the 7 per-pair ACFs with the reference's presence semantics.
+
+    wrapped [A,3,F] wrapped coords (cuda), pair_i/pair_j int32 atom labels (i < j).
+    Returns (G [7,F] float64 cuda — NOT yet scaled by 2/N_spins, hit [F] bool cuda,
+    n_spins int, info dict).  With torch.distributed initialised and shard=True the pairs are
+    split over the ranks and the result is all-reduced (every rank returns the total)."""
+    dev = wrapped.device
+    A, _, F = wrapped.shape
+    P = int(pair_i.numel())
+    M = ops.fft_length(F)
+    lo, hi = dist.shard_range(P) if shard else (0, P)
+    pi, pj = pair_i[lo:hi].contiguous(), pair_j[lo:hi].contiguous()
+    G = torch.zeros((7, F), dtype=torch.float64, device=dev)
+    hit = torch.zeros(F, dtype=torch.int32, device=dev)
+    label_used = torch.zeros(A, dtype=torch.int32, device=dev)
+    info = dict(pairs=P, full=0, partial=0, absent=0, M=M)
+    if hi > lo:
+        if gapless(cell, rmax):
+            full_i, full_j = pi, pj
+            part_i = part_j = None
+            hit.fill_(1)
+            info["full"] = hi - lo
+        else:
+            counts = ops.dd_pair_count(wrapped, pi, pj, cell, rmax, frame_hit=hit)
+            full = counts == F
+            part = (counts > 0) & ~full
+            full_i, full_j = pi[full].contiguous(), pj[full].contiguous()
+            part_i, part_j = pi[part].contiguous(), pj[part].contiguous()
+            info["full"] = int(full.sum())
+            info["partial"] = int(part.sum())
+            info["absent"] = (hi - lo) - info["full"] - info["partial"]
+        if full_i.numel():
+            spec = ops.dd_pairs_to_spectrum(wrapped, full_i, full_j, cell, M=M)
+            G += ops.ifft_acf(spec, F, 1.0 / (float(M) * float(F)))
+            label_used[full_i.long()] = 1
+            label_used[full_j.long()] = 1
+        if part_i is not None and part_i.numel():
+            ops.dd_pairs_ragged_to_acf(wrapped, part_i, part_j, cell, rmax, M=M, G=G)
+            label_used[part_i.long()] = 1
+            label_used[part_j.long()] = 1
+    if shard:
+        dist.allreduce_sum_(G)
+        dist.allreduce_sum_(hit)
+        dist.allreduce_sum_(label_used)
+        cnt = torch.tensor([info["full"], info["partial"], info["absent"]], dtype=torch.int64, device=dev)
+        dist.allreduce_sum_(cnt)
+        info["full"], info["partial"], info["absent"] = (int(v) for v in cnt.tolist())
+    n_spins = int((label_used > 0).sum())
+    return G, hit > 0, n_spins, info
+
+
+def spec_dens_extr_narr(time, G, simpson_mode="cartwright"):
+    """ddrax.py:186-222 (cutoff=False): j_2m = 2*simpson(G_2m, x=time); <F^2_m> = G_2m(0); tau's.
+
+    time [n] and G [7,n] are device tensors (rows in G_COLUMNS order); returns a dict of floats."""
+    y = G[4:7].contiguous()
+    j = (2.0 * ops.simpson(y, time.contiguous(), simpson_mode)).cpu().numpy()
+    f = G[4:7, 0].cpu().numpy()
+    g = {'$j_{2,0}$': float(j[0]), '$j_{2,1}$': float(j[1]), '$j_{2,2}$': float(j[2])}
+    g[r'$\langle F^{2}_{0}\rangle$'] = float(f[0])
+    g[r'$\langle F^{2}_{1}\rangle$'] = float(f[1])
+    g[r'$\langle F^{2}_{2}\rangle$'] = float(f[2])
+    g[r'$\langle F(0)^{2}\rangle$'] = (float(f[1]) + float(f[2])) / 2
+    g[r'$\tau_{0}$'] = g['$j_{2,0}$'] / float(f[0])
+    g[r'$\tau_{1}$'] = g['$j_{2,1}$'] / float(f[1])
+    g[r'$\tau_{2}$'] = g['$j_{2,2}$'] / float(f[2])
+    g[r'$\tau_{c}$'] = (g[r'$\tau_{1}$'] + g[r'$\tau_{2}$']) / 2
+    return g
+
+
+def dipolar(spec_dens, symbol1, symbol2='H'):
+    """ddrax.py:224-274, extreme-narrowing branch (the only one the CLI reaches)."""
+    s = nuc[symbol1]['I']
+    gamma1 = nuc[symbol1]['gamma']
+    gamma2 = nuc[symbol2]['gamma']
+    C_d = (MU_0 / (4 * math.pi)) ** 2 * (gamma1 ** 2) * (gamma2 ** 2) * (HBAR ** 2)
+    s_const = s * (s + 1)
+    au_m = 5.29177e-11
+    j0 = j1 = j2 = float(np.mean([spec_dens['$j_{2,0}$'], spec_dens['$j_{2,1}$'], spec_dens['$j_{2,2}$']]))
+    tc = spec_dens['$\\tau_{c}$']
+    f = C_d * s_const * au_m ** (-6) * spec_dens[r'$\langle F^{2}_{0}\rangle$']
+    if symbol1 == symbol2:
+        R = float(np.real(C_d * s_const * (j1 + (4 * j2)) * au_m ** (-6) * 1e-12))
+    else:
+        R = (2 / 3) * C_d * s_const * 10 * float(np.real(j0)) * au_m ** (-6) * 1e-12
+    return R, tc, f

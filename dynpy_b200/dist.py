@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), independent series sharded by
+contiguous blocks, ONE all-reduce of the accumulated spectra.
+
+Nothing here touches the data path between kernels: every rank transforms its own shard
+with the same kernels; the only exchange is ``all_reduce(SUM)`` of ``[n_acc, M]`` doubles
+(NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, world, local_rank); initialises torch.distributed when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def rank_world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int | None = None, world: int | None = None) -> tuple[int, int]:
+    """Contiguous, balanced block [lo, hi) of n independent units for this rank.
+    Blocks are multiples of 2 units where possible so real-series pair packing stays aligned."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    pairs = (n + 1) // 2
+    lo = (pairs * rank) // world * 2
+    hi = (pairs * (rank + 1)) // world * 2
+    return min(lo, n), min(hi, n)
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place SUM over ranks (no-op for a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

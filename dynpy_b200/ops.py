@@ -105,6 +105,26 @@ def ifft_acf(spectrum, n_out: int, scale: float):
     return acf
 
 
+def wk_acf_each(re, im=None, M=None, ws_budget: int = 2 << 30):
+    """Per-series wiener_khinchin: re (+ i im) [S, N] -> acf [S, N]."""
+    lib = _lib.load()
+    re = _chk(re, torch.float64, "re")
+    S, N = re.shape
+    if im is not None:
+        im = _chk(im, torch.float64, "im")
+    M = fft_length(N) if M is None else int(M)
+    acf = torch.empty((S, N), dtype=torch.float64, device=re.device)
+    one = int(lib.dynpy_wk_each_workspace_bytes(M, 1))
+    n = max(1, min(S, ws_budget // one))
+    with torch.cuda.device(re.device):
+        wsb = int(lib.dynpy_wk_each_workspace_bytes(M, n))
+        ws = workspace(re.device, wsb)
+        rc = lib.dynpy_wk_acf_each_f64(re.data_ptr(), im.data_ptr() if im is not None else None, S, N, N,
+                                       acf.data_ptr(), M, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dynpy_wk_acf_each_f64")
+    return acf
+
+
 # ------------------------------------------------------------------------------ QR
 def qr_efg_to_spectrum(efg, M=None, spectrum=None):
     """efg [S, 6, N] (Vxx,Vyy,Vzz,Vxy,Vxz,Vyz) -> spectrum [3, M] (R20, R2+-1, R2+-2), accumulated."""
@@ -160,7 +180,26 @@ def pdist_ortho(ux, uy, uz, a, b, c, index, dmax=8.0, stride=1):
     return tuple(t[:k] for t in f) + tuple(t[:k] for t in g)
 
 
-def dd_pair_count(coords, pair_i, pair_j, cell, rmax):
+def topology_check(coords, rcov, bond_extra, expect, cell, dmax):
+    """(mismatching pair-frames, first mismatching frame or -1) of the per-frame bond flags
+    against `expect` [A, A] uint8 (upper triangle used)."""
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    rcov = _chk(rcov, torch.float64, "rcov")
+    expect = _chk(expect, torch.uint8, "expect")
+    A, three, F = coords.shape
+    out = torch.zeros(2, dtype=torch.int64, device=coords.device)
+    with torch.cuda.device(coords.device):
+        rc = lib.dynpy_topology_check_f64(coords.data_ptr(), A, F, rcov.data_ptr(), float(bond_extra),
+                                          expect.data_ptr(), float(cell[0]), float(cell[1]), float(cell[2]),
+                                          float(dmax), out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_topology_check_f64")
+    bad, first = out.tolist()
+    return int(bad), (int(first) if bad else -1)
+
+
+def dd_pair_count(coords, pair_i, pair_j, cell, rmax, frame_hit=None):
+    """Frames in which each pair is inside rmax; optional int32 frame_hit[F] gets 1 where any pair is."""
     lib = _lib.load()
     coords = _chk(coords, torch.float64, "coords")
     pair_i = _chk(pair_i, torch.int32, "pair_i")
@@ -170,7 +209,8 @@ def dd_pair_count(coords, pair_i, pair_j, cell, rmax):
     with torch.cuda.device(coords.device):
         rc = lib.dynpy_dd_pair_count_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), pair_i.numel(),
                                          float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
-                                         counts.data_ptr(), _stream())
+                                         counts.data_ptr(), frame_hit.data_ptr() if frame_hit is not None else None,
+                                         _stream())
     _lib.check(rc, "dynpy_dd_pair_count_f64")
     return counts
 

@@ -1,0 +1,136 @@
+"""Quadrupolar driver — mirror of the reference's qrax.py (QR_module_main :28-96) on top of
+the CUDA path: EFG CSV -> rank-2 spherical components -> Wiener–Khinchin ACFs summed over
+nuclei -> Simpson J(0) -> 1/T1, 1/T2, 1/Tiso, tau_c, <V(0)^2>.  Same parameter class
+(``Quadrupolar{data_set, analyte}``) and CSV outputs (``<stem>-<sym>-relax.csv``, ``-acfs.csv``)."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import dist, ops
+from .config import default_simpson_mode
+from .nuc import E_CHARGE, HBAR, nuc
+
+F_COLUMNS = ['$f_{2,-2}$', '$f_{2,-1}$', '$f_{2,0}$', '$f_{2,1}$', '$f_{2,2}$']
+_DTYPE = {'system': 'category', 'traj': 'i8', 'frame': 'i8', 'time': 'f8', 'label': 'i8', 'symbol': 'category',
+          'Vxx': 'f8', 'Vxy': 'f8', 'Vxz': 'f8', 'Vyx': 'f8', 'Vyy': 'f8', 'Vyz': 'f8', 'Vzx': 'f8', 'Vzy': 'f8',
+          'Vzz': 'f8', 'V11': 'f8', 'V22': 'f8', 'V33': 'f8', 'eta': 'f8'}
+_COMPS = ['Vxx', 'Vyy', 'Vzz', 'Vxy', 'Vxz', 'Vyz']
+
+
+def read_efg_data(file_path, dtype=None):
+    """qrax.py:98-112"""
+    return pd.read_csv(file_path, dtype=dtype)
+
+
+def _interpolate(a):
+    """pd.Series.interpolate() semantics of wiener_khinchin (qrax.py:149-150), applied only when
+    a series actually holds NaNs (input cleaning, not part of the hot path)."""
+    ok = ~np.isnan(a)
+    if ok.all() or not ok.any():
+        return a
+    idx = np.arange(len(a))
+    first = idx[ok][0]
+    a = a.copy()
+    a[first:] = np.interp(idx[first:], idx[ok], a[ok])
+    return a
+
+
+def efg_acf_mean(efg: torch.Tensor, shard=True):
+    """efg [S,6,N] cuda -> mean over the S nuclei of the five ACFs f_{2,m}, m=-2..2: [5,N] cuda
+    (cart_to_spatial + groupby('label').apply(correlate) + mean over labels, qrax.py:59-63)."""
+    S, _, N = efg.shape
+    M = ops.fft_length(N)
+    lo, hi = dist.shard_range(S) if shard else (0, S)
+    spec = torch.zeros((3, M), dtype=torch.float64, device=efg.device)
+    if hi > lo:
+        ops.qr_efg_to_spectrum(efg[lo:hi].contiguous(), M=M, spectrum=spec)
+    if shard:
+        dist.allreduce_sum_(spec)
+    acf = ops.ifft_acf(spec, N, 1.0 / (float(M) * float(N) * float(S)))  # rows: R20, R2+-1, R2+-2
+    return acf[[2, 1, 0, 1, 2]].contiguous()
+
+
+def spectral_dens(time, f, simpson_mode="cartwright"):
+    """qrax.py:169-201 (cutoff=False): g_2m = simpson(f_2m, x=time); g_iso = mean. Device tensors in."""
+    g = ops.simpson(f.contiguous(), time.contiguous(), simpson_mode).cpu().numpy()
+    return [float(x) for x in g], float(np.mean(g))
+
+
+def relaxation(g, giso, analyte):
+    """qrax.py:218-233"""
+    quad_mom = nuc[analyte]['Q']
+    s = nuc[analyte]['I']
+    C_q = E_CHARGE * quad_mom / HBAR
+    s_const = (2 * s + 3) / (s ** 2 * (2 * s - 1))
+    au_q = 9.71736408e21
+    gm2, gm1, g0_, gp1, gp2 = g
+    g0 = 4 * gp2 + gp1 + gm1 + 4 * gm2
+    g1 = 2 * gm2 + 3 * gm1 + 2 * gp1 + 3 * g0_
+    gg = 10 * giso
+    k = (1 / 40) * C_q ** 2 * s_const
+    return k * g0 * au_q ** 2 * 1e-12, k * g1 * au_q ** 2 * 1e-12, k * gg * au_q ** 2 * 1e-12
+
+
+def QR_module_main(QR, label=None, device=None):
+    rawdf = read_efg_data(QR.data_set, dtype=_DTYPE)
+    symbol = "".join([char for char in QR.analyte if char.isalpha()])
+    simpson_mode = getattr(QR, 'simpson_mode', None) or default_simpson_mode()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    rank, world = dist.rank_world()
+    ACFs, res = {}, {}
+    for traj, df in rawdf.groupby('traj'):
+        if traj == 0:
+            continue
+        df = df.sort_values(by='time')
+        df['frame'] = df['frame'] - df.frame.iloc[0]
+        df['time'] = df['time'] - df.time.iloc[0]
+        if label:
+            adf = df[df['label'] == int(label)]
+        else:
+            adf = df[df['symbol'] == symbol]
+        labels = sorted(adf['label'].unique().tolist())
+        series = {lab: adf[adf['label'] == lab] for lab in labels}
+        lengths = {len(v) for v in series.values()}
+        if len(lengths) != 1:
+            raise ValueError("nuclei of trajectory %r have EFG series of different lengths %s" % (traj, sorted(lengths)))
+        N = lengths.pop()
+        host = np.empty((len(labels), 6, N), dtype=np.float64)
+        for k, lab in enumerate(labels):
+            for c, name in enumerate(_COMPS):
+                host[k, c] = _interpolate(series[lab][name].to_numpy(dtype=np.float64))
+        first = series[labels[0]]
+        frame = np.mean([series[lab]['frame'].to_numpy(dtype=np.float64) for lab in labels], axis=0)
+        tm = np.mean([series[lab]['time'].to_numpy(dtype=np.float64) for lab in labels], axis=0)
+        f = efg_acf_mean(torch.from_numpy(host).to(device))
+        tdev = torch.from_numpy(tm).to(device)
+        g, giso = spectral_dens(tdev, f, simpson_mode)
+        fh = f.cpu().numpy()
+        v0 = float(fh[:, 0].sum())
+        t1, t2, tiso = relaxation(g, giso, QR.analyte)
+        acf_mean = pd.DataFrame({'frame': frame, 'time': tm})
+        for c, name in enumerate(F_COLUMNS):
+            acf_mean[name] = fh[c]
+        acf_mean['symbol'] = symbol
+        acf_mean.index = pd.Index(frame, name='frame')
+        ACFs[traj] = acf_mean
+        res[traj] = pd.DataFrame.from_dict({'symbol': [symbol], r'$\frac{1}{T_{1}}$': [t1],
+                                            r'$\frac{1}{T_{2}}$': [t2], r'$\frac{1}{T_{iso}}$': [tiso],
+                                            '$\\tau_{c}$': [giso * 5 / v0], r'$\langle V(0)^2\rangle$': [v0]})
+        del first
+    rax = pd.concat(res)
+    rax.index = rax.index.droplevel(level=1)
+    rax_mean = pd.DataFrame(rax.mean(numeric_only=True)).T
+    rax_mean.index = ["mean"]
+    rax_sem = pd.DataFrame(rax.sem(numeric_only=True)).T
+    rax_sem.index = ["err"]
+    all_rax = pd.concat([rax, rax_mean, rax_sem], sort=False)
+    acfs = pd.concat(ACFs)
+    system = QR.data_set.split('.csv')[0]
+    if rank == 0:
+        all_rax.to_csv(system + "-" + symbol + "-relax.csv", index_label="traj")
+        acfs.to_csv(system + "-" + symbol + "-acfs.csv", index=False)
+        print("Results written to " + system + "-" + symbol + "-relax.csv")
+    return all_rax, acfs

@@ -1,0 +1,155 @@
+"""Bonds, molecules and labels — the indexing the reference derives with
+compute_atom_two/_compute_bonds (distances.py:68-103,244-257), compute_molecule
+(universe.py:411-451), Molecule.classify (universe.py:340-384) and get_atom_labels
+(universe.py:107-118).
+
+The reference rebuilds a networkx graph over the atoms of ALL frames.  Here the pair list of
+a frame comes from the bit-exact CUDA pdist_ortho kernel, the (tiny) union-find runs on the
+host once, and the bond list is re-checked on a few other frames: a molecular-dynamics
+topology that changes mid-trajectory is reported instead of silently mis-indexed.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+import torch
+
+from . import ops
+from .elements import SYM2COVRAD, SYM2MASS
+
+
+def parse_formula(identifier: str) -> dict:
+    """'H(2)O(1)' -> {'H': 2, 'O': 1}"""
+    out = {}
+    for sym, cnt in re.findall(r"([A-Z][a-z]?)\((\d+)\)", identifier):
+        out[sym] = out.get(sym, 0) + int(cnt)
+    if not out:
+        raise KeyError("cannot parse molecular formula %r" % identifier)
+    return out
+
+
+def atoms_per_formula(identifier: str) -> int:
+    """nat_per_mol exactly as DDparse.py:151 / SRparse.py:158 compute it."""
+    return int(np.sum([int(n) for n in identifier.replace('(', ')').split(')') if n.isnumeric()]))
+
+
+def frame_pairs(wrapped: torch.Tensor, cell, frame: int, dmax: float):
+    """pdist_ortho of one frame of wrapped coords [A,3,F] -> dict of host arrays
+    (i, j = atom labels inside the frame, row-major upper triangle order)."""
+    A, _, F = wrapped.shape
+    idx = torch.arange(A, dtype=torch.int64, device=wrapped.device)
+    dx, dy, dz, dr, a0, a1, prj = ops.pdist_ortho(wrapped[:, 0, frame], wrapped[:, 1, frame], wrapped[:, 2, frame],
+                                                  cell[0], cell[1], cell[2], idx, dmax, stride=3 * F)
+    return dict(dx=dx.cpu().numpy(), dy=dy.cpu().numpy(), dz=dz.cpu().numpy(), dr=dr.cpu().numpy(),
+                i=a0.cpu().numpy(), j=a1.cpu().numpy(), prj=prj.cpu().numpy())
+
+
+def bonded(two: dict, symbols, bond_extra: float = 0.45) -> np.ndarray:
+    """bond flag per row: dr <= rcov(a) + rcov(b) + bond_extra (distances.py:244-257)."""
+    rc = np.array([SYM2COVRAD[s] for s in symbols], dtype=np.float64)
+    return two["dr"] <= (rc[two["i"]] + rc[two["j"]] + bond_extra)
+
+
+class Topology:
+    """Molecules of one frame in the reference's numbering.
+
+    mol_rank[a] : molecule index inside the frame in networkx discovery order — isolated atoms
+                  first (atom order), then connected components ordered by their smallest atom.
+    groups      : list (by mol_rank) of atom-label tuples (ascending).
+    """
+
+    def __init__(self, nat: int, bi: np.ndarray, bj: np.ndarray, symbols):
+        parent = list(range(nat))
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+
+        deg = np.zeros(nat, dtype=np.int64)
+        for a, b in zip(bi.tolist(), bj.tolist()):
+            deg[a] += 1
+            deg[b] += 1
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+        self.nat = nat
+        self.symbols = list(symbols)
+        self.mol_rank = np.full(nat, -1, dtype=np.int64)
+        k = 0
+        for a in range(nat):
+            if deg[a] == 0:
+                self.mol_rank[a] = k
+                k += 1
+        self.n_isolated = k
+        seen = {}
+        for a in range(nat):
+            if deg[a] == 0:
+                continue
+            r = find(a)
+            if r not in seen:
+                seen[r] = k
+                k += 1
+            self.mol_rank[a] = seen[r]
+        self.nmol = k
+        self.groups = [[] for _ in range(k)]
+        for a in range(nat):
+            self.groups[self.mol_rank[a]].append(a)
+        self.groups = [tuple(g) for g in self.groups]
+        self.bonds = set(zip(bi.tolist(), bj.tolist()))
+
+    def formula(self, m: int) -> dict:
+        out = {}
+        for a in self.groups[m]:
+            out[self.symbols[a]] = out.get(self.symbols[a], 0) + 1
+        return out
+
+    def classify_exact(self, identifier: str) -> np.ndarray:
+        """bool per molecule: formula == identifier (Molecule.classify with exact=True).
+        Raises KeyError like the reference when nothing matches (universe.py:378)."""
+        want = parse_formula(identifier)
+        syms = sorted({s for s in self.symbols})
+        hit = np.array([all(self.formula(m).get(s, 0) == want.get(s, 0) for s in set(syms) | set(want))
+                        for m in range(self.nmol)], dtype=bool)
+        if not hit.any():
+            raise KeyError('No records found for {}, with identifier {}.'.format("analyte", want))
+        return hit
+
+    def molecule_id(self, frame_index: int, m: int, nframes: int) -> int:
+        """Global 'molecule' id the reference would assign (universe.py:426-437) for a topology
+        that is the same in every frame: all isolated atoms of all frames first, then components."""
+        if m < self.n_isolated:
+            return frame_index * self.n_isolated + m
+        n_multi = self.nmol - self.n_isolated
+        return nframes * self.n_isolated + frame_index * n_multi + (m - self.n_isolated)
+
+    def masses(self, atoms) -> np.ndarray:
+        return np.array([SYM2MASS[self.symbols[a]] for a in atoms], dtype=np.float64)
+
+
+def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra: float = 0.45,
+                   check_frames=None) -> tuple[Topology, dict]:
+    """Topology from frame 0 (+ consistency check on `check_frames`, default middle and last)."""
+    A, _, F = wrapped.shape
+    two0 = frame_pairs(wrapped, cell, 0, dmax)
+    b0 = bonded(two0, symbols, bond_extra)
+    topo = Topology(A, two0["i"][b0], two0["j"][b0], symbols)
+    if check_frames is None:  # every frame, on the device
+        expect = torch.zeros((A, A), dtype=torch.uint8)
+        expect[torch.from_numpy(two0["i"][b0]), torch.from_numpy(two0["j"][b0])] = 1
+        rc = torch.tensor([SYM2COVRAD[s] for s in symbols], dtype=torch.float64, device=wrapped.device)
+        bad, first = ops.topology_check(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
+        if bad:
+            raise RuntimeError("bond topology changes along the trajectory (%d pair-frames differ from frame index 0, "
+                               "first at frame index %d): dynpy_b200 indexes molecules from a static topology, the "
+                               "reference would re-detect molecules in every frame" % (bad, first))
+        return topo, two0
+    for f in check_frames:
+        two = frame_pairs(wrapped, cell, f, dmax)
+        b = bonded(two, symbols, bond_extra)
+        if set(zip(two["i"][b].tolist(), two["j"][b].tolist())) != topo.bonds:
+            raise RuntimeError("bond topology of frame index %d differs from frame 0: dynpy_b200 indexes molecules "
+                               "from a static topology (the reference would re-detect molecules per frame)" % f)
+    return topo, two0

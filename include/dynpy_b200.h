@@ -48,6 +48,13 @@ const char* dynpy_last_error(void);
 /* number of SMs of the current device (grids are sized in multiples of it); <0 on error */
 int dynpy_device_sm_count(void);
 
+/* Optional per-kernel-class device timing (CUDA events on the launching stream), for live
+ * roofline numbers: classes 0 dipolar word generator, 1 FFT column pass, 2 FFT row pass, 3 other.
+ * dynpy_profile_read synchronises the device, returns the summed milliseconds and launch counts
+ * since the previous read (host arrays of 4) and resets them. */
+int dynpy_profile_enable(int on);
+int dynpy_profile_read(double* ms_host, int64_t* launches_host);
+
 /* Padded transform length used for a series of n samples: max(32, 2^ceil(log2(2n))).
  * Any M >= 2n-1 gives the same linear ACF as the reference's n=2N (qrax.py:153). */
 int64_t dynpy_fft_length(int64_t n);
@@ -76,6 +83,14 @@ int dynpy_wk_acf_sum_f64(const double* re, const double* im, int64_t n_series, i
 int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf, int64_t n_out,
                        double scale, void* ws, int64_t ws_bytes, dynpy_stream_t stream);
 
+/* Per-series variant (no sum): acf[s][k] = wiener_khinchin(series_s)[k], k < n — what
+ * correlate() returns per group when the individual ACFs are written out
+ * (Jacfs_all.csv, SRparse.py:82,89). */
+int64_t dynpy_wk_each_workspace_bytes(int64_t M, int64_t n_series);
+int dynpy_wk_acf_each_f64(const double* re, const double* im, int64_t n_series, int64_t n,
+                          int64_t series_stride, double* acf, int64_t M, void* ws, int64_t ws_bytes,
+                          dynpy_stream_t stream);
+
 /* ---- quadrupolar --------------------------------------------------------------------------
  * replaces cart_to_spatial + groupby('label').apply(correlate)  (qrax.py:59-60,115-166):
  * spectrum[3][M] accumulates, over the nuclei of this shard, the power spectra of
@@ -100,12 +115,22 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
                           int64_t* atom0, int64_t* atom1, int64_t* projection, int64_t* count,
                           void* ws, int64_t ws_bytes, dynpy_stream_t stream);
 
+/* Static-topology check: the reference re-detects bonds (dr <= rcov0 + rcov1 + bond_extra among
+ * pairs with dr < dmax, distances.py:244-257) and molecules in EVERY frame; the CUDA path
+ * indexes molecules once.  This verifies the equivalence: expect[i*n_atoms + j] (i<j) is the bond
+ * flag of the indexing frame; out[0] = mismatching pair-frames, out[1] = first such frame
+ * (UINT64_MAX if none).  coords WRAPPED. */
+int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                             const double* rcov, double bond_extra, const uint8_t* expect, double a,
+                             double b, double c, double dmax, uint64_t* out, dynpy_stream_t stream);
+
 /* frames in which each pair's minimum-image distance is < rmax  (the presence rule of
- * compute_atom_two, DDparse.py:148): counts[p] in [0, n_frames]. coords are WRAPPED. */
+ * compute_atom_two, DDparse.py:148): counts[p] in [0, n_frames]. coords are WRAPPED.
+ * frame_hit (optional, [n_frames], caller-zeroed) is set to 1 where any pair is present. */
 int dynpy_dd_pair_count_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
                             const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
                             double a, double b, double c, double rmax, int64_t* counts,
-                            dynpy_stream_t stream);
+                            int32_t* frame_hit, dynpy_stream_t stream);
 
 /* Fused dipolar path for pairs present in every frame; replaces pdist_ortho per frame +
  * cart_to_dipolar_from_df + groupby(pair).apply(correlate) + the pair sum
