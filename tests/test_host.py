@@ -1,0 +1,228 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), the CLI contract, trajectory parsing, topology/pair indexing
+against the oracle, and the multi-rank plumbing (world_size 2, gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_params
+from oracle import oracle_np as orc
+
+
+# ------------------------------------------------------------------ C-ABI surface
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "dynpy_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dynpy_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dynpy_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    names = _header_functions()
+    assert len(names) >= 20
+    assert sorted(_lib.SIGNATURES) == names, set(_lib.SIGNATURES) ^ set(names)
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dynpy_version() >= 100
+    # pure host helpers may be called without a GPU
+    assert lib.dynpy_fft_length(316) == 1024
+    assert lib.dynpy_fft_length(100000) == 262144
+    assert lib.dynpy_fft_length(1) == 32
+    assert lib.dynpy_fft_workspace_bytes(4096, 10) == 0
+    assert lib.dynpy_fft_workspace_bytes(8192, 3) == 3 * 8192 * 16
+
+
+def test_no_cpu_fallback():
+    from dynpy_b200 import _lib, ops
+    with pytest.raises(_lib.DynpyError, match="CUDA tensor"):
+        ops.wk_acf_sum(torch.zeros((2, 16), dtype=torch.float64))
+    with pytest.raises(_lib.DynpyError, match="CUDA tensor"):
+        ops.wrap(torch.zeros(4, dtype=torch.float64), 3.0)
+    if not torch.cuda.is_available():  # a compute entry point without a device must fail loudly
+        lib = _lib.load()
+        assert lib.dynpy_device_sm_count() < 0
+        assert b"CUDA" in lib.dynpy_last_error() or b"device" in lib.dynpy_last_error()
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dynpy_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            txt = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
+            assert "oracle_np" not in txt and "refshim" not in txt, fn
+    assert "oracle" not in open(os.path.join(ROOT, "dynpy.py")).read()
+
+
+# ------------------------------------------------------------------ CLI contract (dynpy.py:42-124)
+def _cli(args, cwd):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    return subprocess.run([sys.executable, "-m", "dynpy"] + args, cwd=cwd, text=True, capture_output=True, env=env,
+                          timeout=300)
+
+
+def test_cli_contract(tmp_path):
+    (tmp_path / "params.py").write_text("class Quadrupolar:\n    data_set = 'x.csv'\n")
+    r = _cli(["-q", "params.py"], tmp_path)
+    assert r.returncode == 2 and "Error: Missing required input variable analyte in class Quadrupolar." in r.stdout
+    r = _cli(["--nonsense"], tmp_path)
+    assert r.returncode == 2 and r.stdout.startswith("USAGE:")
+    r = _cli([], tmp_path)
+    assert r.returncode == 2 and r.stdout.startswith("USAGE:")
+    r = _cli(["-h"], tmp_path)
+    assert r.returncode == 0 and "--DDrelax <params.py>" in r.stdout
+    r = _cli(["-d", "nofile.py"], tmp_path)
+    assert r.returncode == 2 and "Input parameter file must have .py file extension" in r.stdout
+    (tmp_path / "dd.py").write_text("class ParseDynamics:\n    MD_format='xyz'\nclass Dipolar:\n    identifier='H(2)O(1)'\n")
+    r = _cli(["--DDrax", "dd.py"], tmp_path)  # BASELINE.json spelling is an alias
+    assert r.returncode == 2 and "Missing required input variable traj_dir in class ParseDynamics" in r.stdout
+
+
+# ------------------------------------------------------------------ trajectory ingestion
+@pytest.mark.parametrize("case", ["dd_gapless_all", "dd_intra_sampled", "sr_methane"])
+def test_parse_xyz_matches_reference_semantics(case):
+    from dynpy_b200 import parseMD
+    P = load_params(case)
+    PD = P.ParseDynamics
+    PD.traj_dir = os.path.join(GOLDEN, case) + "/"
+    tr = parseMD.PARSE_MD(PD, "01", device=torch.device("cpu"))
+    pos, sym, frames = orc.read_xyz(os.path.join(GOLDEN, case, "01", "traj.xyz"), PD.nat, PD.start_prod, PD.end_prod,
+                                    PD.sample_freq, PD.md_print_freq)
+    assert tr.symbols == sym
+    np.testing.assert_array_equal(tr.frames, frames)
+    np.testing.assert_array_equal(tr.pos.numpy(), pos.transpose(1, 2, 0))
+
+
+def test_parse_tinker_arc(tmp_path):
+    from dynpy_b200 import parseMD, synth
+    box = synth.water_box(4, seed=1)
+    traj = box.frames(0, 5).numpy() / synth.BOHR_PER_ANG
+    d = tmp_path / "01"
+    d.mkdir()
+    with open(d / "water.arc", "w") as fh:
+        for f in range(5):
+            fh.write("%6d  water box\n   20.0 20.0 20.0 90.0 90.0 90.0\n" % box.nat)
+            for a in range(box.nat):
+                s = ("OW", "HW", "H2")[a % 3]
+                x, y, z = traj[a, :, f]
+                fh.write(("%6d  %-3s%14.8f%14.8f%14.8f %5d %5d\n" % (a + 1, s, x, y, z, 1, 2)).replace("E", "D"))
+
+    class PD:
+        MD_format = "Tinker"; traj_dir = str(tmp_path) + "/"; trajs = ["01"]; nat = box.nat; start_prod = 2
+        end_prod = 4; md_print_freq = 10; sample_freq = 2; celldm = 20.0; timestep = 0.001
+    tr = parseMD.PARSE_MD(PD, "01", device=torch.device("cpu"))
+    assert tr.symbols[:3] == ["O", "H", "H"]
+    np.testing.assert_array_equal(tr.frames, [20, 40])
+    np.testing.assert_allclose(tr.pos.numpy()[:, :, 0], np.round(traj[:, :, 1], 8) / 0.529177, rtol=0, atol=1e-12)
+
+
+# ------------------------------------------------------------------ topology / pair indexing
+def test_topology_numbering_and_pair_selection_match_oracle():
+    from dynpy_b200 import DDparse, synth, topology
+    box = synth.water_box(8, seed=2)
+    pos = box.frames(0, 3).numpy().transpose(2, 0, 1)
+    two, mol = orc.atom_two_table(pos, box.symbols, box.celldm, 15.0)
+    f0 = two["f"] == 0
+    b = two["bond"] & f0
+    topo = topology.Topology(box.nat, two["i"][b], two["j"][b], box.symbols)
+    np.testing.assert_array_equal(topo.mol_rank, mol[0])
+    assert topo.nmol == 8 and topo.n_isolated == 0
+    assert topo.molecule_id(2, 5, 3) == mol[2][topo.groups[5][0]]
+    assert topo.classify_exact("H(2)O(1)").all()
+    with pytest.raises(KeyError):
+        topo.classify_exact("H(4)C(1)")
+    # isolated atoms are numbered first (universe.py:426-431)
+    t2 = topology.Topology(5, np.array([1]), np.array([3]), ["Na", "O", "Cl", "H", "K"])
+    np.testing.assert_array_equal(t2.mol_rank, [0, 3, 1, 3, 2])
+    assert t2.molecule_id(1, 3, 10) == 10 * 3 + 1 * 1 + 0
+    for ptype, alabel in (("all", None), ("intra", None), ("inter", None), ("all", 1), ("all", 0)):
+        pi, pj = DDparse.select_pairs(box.symbols, topo, 3, ptype, alabel)
+        sym = np.array(box.symbols)
+        i, j = two["i"][f0], two["j"][f0]
+        if alabel:
+            sel = ((i % 3) == alabel) & (sym[j] == "H")
+        else:
+            sel = (sym[i] == "H") & (sym[j] == "H")
+        if ptype == "intra":
+            sel &= mol[0][i] == mol[0][j]
+        if ptype == "inter":
+            sel &= mol[0][i] != mol[0][j]
+        np.testing.assert_array_equal(pi, i[sel])
+        np.testing.assert_array_equal(pj, j[sel])
+    assert topology.atoms_per_formula("H(3)C(2)N(1)") == 6
+    assert topology.parse_formula("H(2)O(1)") == {"H": 2, "O": 1}
+
+
+def test_sr_frame_step_quirk():
+    from dynpy_b200 import SRparse
+    assert SRparse.frame_step(np.array([4, 6, 8, 10]), 5) == 2
+    assert SRparse.frame_step(np.array([4, 6, 9]), 5) == 3          # last *new* distinct diff
+    assert SRparse.frame_step(np.array([4, 6, 9, 11]), 5) == 3      # 2 was already seen
+    assert SRparse.frame_step(np.array([4, 6]), 1) == 2
+
+
+def test_simpson_mode_default_follows_scipy():
+    from dynpy_b200 import config
+    import scipy
+    maj, mnr = (int(x) for x in scipy.__version__.split(".")[:2])
+    assert config.default_simpson_mode() == ("cartwright" if (maj, mnr) >= (1, 11) else "avg")
+    os.environ["DYNPY_SIMPSON"] = "avg"
+    try:
+        assert config.default_simpson_mode() == "avg"
+    finally:
+        del os.environ["DYNPY_SIMPSON"]
+
+
+# ------------------------------------------------------------------ multi-rank plumbing
+def test_shard_range_partitions_everything():
+    from dynpy_b200 import dist
+    for n in (0, 1, 2, 7, 130816, 523264):
+        for world in (1, 2, 3, 8):
+            cuts = [dist.shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                assert a[1] == b[0] and a[0] % 2 == 0
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 2
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from dynpy_b200 import dist
+from oracle import oracle_np as orc
+rank, world, local = dist.init_from_env("gloo")
+rng = np.random.default_rng(0)
+x = rng.normal(size=(11, 64))
+lo, hi = dist.shard_range(11)
+# each rank sums the ACFs of its shard (CPU stand-in for the per-rank spectrum), then ONE all-reduce
+part = np.zeros(64)
+for s in range(lo, hi):
+    part += orc.wiener_khinchin(x[s])
+t = torch.from_numpy(part)
+dist.allreduce_sum_(t)
+ref = sum(orc.wiener_khinchin(x[s]) for s in range(11))
+assert np.allclose(t.numpy(), ref, rtol=0, atol=1e-12), "rank %%d mismatch" %% rank
+dist.barrier()
+print("rank", rank, "of", world, "shard", lo, hi, "ok")
+"""
+
+
+def test_two_rank_gloo_allreduce(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    port = 29000 + os.getpid() % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2, r.stdout
