@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdynpy_b200.so")
+LIB_PATH = os.environ.get("DYNPY_B200_LIB") or os.path.join(_HERE, "csrc", "libdynpy_b200.so")
 
 p = C.c_void_p
 i64 = C.c_int64

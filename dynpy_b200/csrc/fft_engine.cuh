@@ -30,6 +30,12 @@ typedef double2 cd;
 typedef long long i64;
 
 #define DYNPY_ROW_LEN 4096  // M2 of the two-pass split
+#ifndef DYNPY_ROWS_MINB
+#define DYNPY_ROWS_MINB 2   // resident CTAs per SM the row kernel is compiled for
+#endif
+#ifndef DYNPY_COLS_MINB
+#define DYNPY_COLS_MINB 2   // same for the column kernel
+#endif
 
 __device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -190,6 +196,19 @@ struct PlanarLoader {
         double b = c.i ? (__ldg(c.i + n) - c.bi) : 0.0;
         return make_double2(a * c.sc, b * c.sc);
     }
+    // two-phase form: raw() only issues the loads (so a whole batch can be in flight), finish()
+    // does the arithmetic.  Out-of-range samples read as the bias, i.e. 0 after finish().
+    __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const {
+        cd v = make_double2(c.br, c.bi);
+        if (n < c.n) {
+            v.x = __ldg(c.r + n);
+            if (c.i) v.y = __ldg(c.i + n);
+        }
+        return v;
+    }
+    __device__ __forceinline__ cd finish(const Ctx& c, cd v) const {
+        return make_double2((v.x - c.br) * c.sc, (v.y - c.bi) * c.sc);
+    }
 };
 
 // Quadrupolar loader (qrax.py:115-145): EFG stored [nucleus][6][N] with component order
@@ -225,6 +244,8 @@ struct QrLoader {
         if (c.slot == 1 || c.slot == 3) return make_double2(__ldg(p + 4 * N + n), -__ldg(p + 5 * N + n));
         return make_double2(0.5 * (__ldg(p + n) - __ldg(p + N + n)), -__ldg(p + 3 * N + n));
     }
+    __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const { return load(c, n); }
+    __device__ __forceinline__ cd finish(const Ctx& c, cd v) const { return v; }
 };
 
 // Final transform: reads the accumulated spectrum S' (internal order) of accumulator f as a
@@ -239,6 +260,8 @@ struct SpectrumLoader {
         i64 idx = (M1 > 1) ? (n % M1) * (i64)DYNPY_ROW_LEN + n / M1 : n;
         return make_double2(__ldg(c.s + idx), 0.0);
     }
+    __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const { return load(c, n); }
+    __device__ __forceinline__ cd finish(const Ctx& c, cd v) const { return v; }
 };
 
 // Row loader for the second pass: T[f_local][k1][n2]
@@ -269,7 +292,7 @@ struct EpiParams {
 // [f0 + blockIdx.y*stride ...]; single pass: the whole transform, M1 == 1).
 // Threads: L / RL (one last-step butterfly each), padded up to a warp.
 template <int L, bool TWO_PASS, class Loader, int MODE>
-__global__ void __launch_bounds__((L / Plan<L>::RL) < 32 ? 32 : (L / Plan<L>::RL))
+__global__ void __launch_bounds__((L / Plan<L>::RL) < 32 ? 32 : (L / Plan<L>::RL), DYNPY_ROWS_MINB)
 k_rows(Loader ld, EpiParams ep, const cd* __restrict__ twp, i64 f_begin, i64 f_end, int f_step, int M1) {
     typedef Plan<L> P;
     constexpr int R1 = P::R1, R2 = P::R2, R3 = P::R3, S = P::S, RL = P::RL;
@@ -388,7 +411,7 @@ k_rows(Loader ld, EpiParams ep, const cd* __restrict__ twp, i64 f_begin, i64 f_e
 // CTA = tile of C consecutive columns n2 of every FFT f = f_begin + blockIdx.y + j*f_step.
 // Threads: (M1/RL) * C, column index fastest (coalesced 8*C-byte loads, 16*C-byte stores).
 template <int M1, int C, class Loader>
-__global__ void __launch_bounds__((M1 / Plan<M1>::RL) * C)
+__global__ void __launch_bounds__((M1 / Plan<M1>::RL) * C, DYNPY_COLS_MINB)
 k_cols(Loader ld, cd* __restrict__ T, const cd* __restrict__ twp, i64 M, double inv_M, i64 f_begin, i64 f_end,
        int f_step) {
     typedef Plan<M1> P;
@@ -421,12 +444,19 @@ k_cols(Loader ld, cd* __restrict__ T, const cd* __restrict__ twp, i64 M, double 
     for (i64 f = f_begin + blockIdx.y; f < f_end; f += f_step) {
         typename Loader::Ctx ctx = ld.begin(f);
         cd v[RL];
-#pragma unroll 1
+        cd in[RL];  // all RL input samples of this thread are requested before any is consumed
+#pragma unroll
+        for (int it = 0; it < RL / R1; ++it) {
+#pragma unroll
+            for (int q = 0; q < R1; ++q)
+                in[it * R1 + q] = ld.raw(ctx, (i64)(q * P1 + bb + it * NB) * M2 + n2);
+        }
+#pragma unroll
         for (int it = 0; it < RL / R1; ++it) {
             const int m = bb + it * NB;
             cd u[R1];
 #pragma unroll
-            for (int q = 0; q < R1; ++q) u[q] = ld.load(ctx, (i64)(q * P1 + m) * M2 + n2);
+            for (int q = 0; q < R1; ++q) u[q] = ld.finish(ctx, in[it * R1 + q]);
             fft_dif<R1>(u);
             if constexpr (S == 1) {
 #pragma unroll
