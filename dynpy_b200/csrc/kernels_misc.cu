@@ -2,6 +2,7 @@
 // pdist_ortho, dipolar word generator, pair presence count, spin-rotation angular momentum,
 // Simpson reduction.  Reference lines are cited per kernel.
 #include "kernels.h"
+#include "dd_device.cuh"
 
 namespace dynpy {
 
@@ -20,17 +21,6 @@ cudaError_t launch_init_twiddles(double2* tw, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ wrap
-// np.mod(x, L) (universe.py:301-304 via distances.modv): C fmod, then the sign fix-up numpy
-// applies (npy_divmod): a non-zero remainder with the wrong sign gets +L (may round to L).
-__device__ __forceinline__ double np_mod(double x, double L) {
-    double m = fmod(x, L);
-    if (m != 0.0) {
-        if ((L < 0.0) != (m < 0.0)) m = __dadd_rn(m, L);
-    } else {
-        m = copysign(0.0, L);
-    }
-    return m;
-}
 __global__ void k_wrap(const double* __restrict__ x, double* __restrict__ out, i64 n, double L) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 stride = (i64)gridDim.x * blockDim.x;
@@ -42,60 +32,6 @@ cudaError_t launch_wrap(const double* x, double* out, i64 n, double L, int n_sm,
     if (blocks > (i64)n_sm * 16) blocks = (i64)n_sm * 16;
     k_wrap<<<(unsigned)blocks, 256, 0, st>>>(x, out, n, L);
     return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------ minimum image
-// Literal restatement of the candidate loop of pdist_ortho (distances.py:203-233): 27 images
-// in (aa,bb,cc) order, pxi = xi + aa*a, d = pxi - xj, r2 = dx*dx + dy*dy + dz*dz left to
-// right, strict '<' against a running best that starts at dmax^2.  __d*_rn blocks FMA
-// contraction so every comparison sees the same bits numba/LLVM produces.
-struct MinImage {
-    double dx, dy, dz, r2;
-    int prj;
-    bool found;
-};
-__device__ __forceinline__ MinImage min_image27(double xi, double yi, double zi, double xj, double yj, double zj,
-                                                double a, double b, double c, double dmax2) {
-    MinImage r;
-    r.dx = r.dy = r.dz = 0.0;
-    r.r2 = dmax2;
-    r.prj = 0;
-    r.found = false;
-    int prj = 0;
-#pragma unroll
-    for (int aa = -1; aa <= 1; ++aa) {
-        const double dpx = __dsub_rn(__dadd_rn(xi, __dmul_rn((double)aa, a)), xj);
-        const double sx = __dmul_rn(dpx, dpx);
-#pragma unroll
-        for (int bb = -1; bb <= 1; ++bb) {
-            const double dpy = __dsub_rn(__dadd_rn(yi, __dmul_rn((double)bb, b)), yj);
-            const double sxy = __dadd_rn(sx, __dmul_rn(dpy, dpy));
-#pragma unroll
-            for (int cc = -1; cc <= 1; ++cc) {
-                const double dpz = __dsub_rn(__dadd_rn(zi, __dmul_rn((double)cc, c)), zj);
-                const double r2 = __dadd_rn(sxy, __dmul_rn(dpz, dpz));
-                if (r2 < r.r2) {
-                    r.dx = dpx; r.dy = dpy; r.dz = dpz; r.r2 = r2; r.prj = prj; r.found = true;
-                }
-                ++prj;
-            }
-        }
-    }
-    return r;
-}
-
-// Per-axis form used inside the fused dipolar generator: the minimum over the 27 sums equals
-// the sum of the per-axis minima bit for bit (fp add is monotone), so presence (r2 < rmax^2)
-// and dr are identical to min_image27; only the image picked under an exact rounding tie
-// of the 27 sums could differ.
-__device__ __forceinline__ void axis_min(double xi, double xj, double a, double& d, double& d2) {
-    const double dm = __dsub_rn(__dsub_rn(xi, a), xj);
-    const double d0 = __dsub_rn(xi, xj);
-    const double dp = __dsub_rn(__dadd_rn(xi, a), xj);
-    const double sm = __dmul_rn(dm, dm), s0 = __dmul_rn(d0, d0), sp = __dmul_rn(dp, dp);
-    d = dm; d2 = sm;
-    if (s0 < d2) { d = d0; d2 = s0; }
-    if (sp < d2) { d = dp; d2 = sp; }
 }
 
 // ------------------------------------------------------------------ pdist_ortho (bit-exact)
@@ -189,35 +125,6 @@ cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i
     k_pdist<true><<<(unsigned)nblocks, 256, 0, st>>>(ux, uy, uz, stride, n, a, b, c, index, dmax2, npairs,
                                                     block_counts, dx, dy, dz, dr, a0, a1, prj);
     return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------ dipolar words
-// ddrax.py:72-126 in Cartesian closed form (no arccos/atan2/sincos):
-//   Y20 = 1/4 sqrt(5/pi) (3 z^2/r^2 - 1)
-//   Y21 = -1/2 sqrt(15/2pi) z (x + i y)/r^2        Y22 = 1/4 sqrt(15/2pi) (x + i y)^2/r^2
-//   r^-3 ;  F2m = sqrt(4 pi/5) Y2m r^-3
-struct DDWords {
-    double y20, y21r, y21i, y22r, y22i, r3, f20, f21r, f21i, f22r, f22i;
-};
-__device__ __forceinline__ DDWords dd_words(double dx, double dy, double dz, double r2) {
-    const double C20 = 0.31539156525252000603;   // (1/4) sqrt(5/pi)
-    const double C21 = -0.77254840404638362;     // -(1/2) sqrt(15/(2 pi))
-    const double C22 = 0.38627420202319181;      // (1/4) sqrt(15/(2 pi))
-    const double KF = 1.5853309190424043;        // sqrt(4 pi/5)
-    DDWords w;
-    double rinv = rsqrt(r2);
-    rinv = rinv * fma(-0.5 * r2, rinv * rinv, 1.5);  // one Newton step: r^-1 to ~1 ulp
-    const double ir2 = rinv * rinv;
-    w.r3 = ir2 * rinv;
-    w.y20 = C20 * (3.0 * dz * dz * ir2 - 1.0);
-    const double zr = dz * ir2;
-    w.y21r = C21 * zr * dx;
-    w.y21i = C21 * zr * dy;
-    w.y22r = C22 * (dx * dx - dy * dy) * ir2;
-    w.y22i = C22 * 2.0 * dx * dy * ir2;
-    const double k = KF * w.r3;
-    w.f20 = k * w.y20; w.f21r = k * w.y21r; w.f21i = k * w.y21i; w.f22r = k * w.y22r; w.f22i = k * w.y22i;
-    return w;
 }
 
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
