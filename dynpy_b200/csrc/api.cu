@@ -1,6 +1,7 @@
 // dynpy_b200 — the C-ABI (include/dynpy_b200.h): argument checks, workspace carving,
 // batch loops.  All compute is in the kernels of fft_engine.cuh / kernels_misc.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -436,6 +437,11 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
     rc = get_device_state(&d, st);
     if (rc) return rc;
     const i64 N = n_frames;
+    {
+        const char* sel = getenv("DYNPY_DD_PATH");  // "v1": previous generation kernels (A/B checks)
+        if (dd2_supported(M) && !(sel && sel[0] == 'v' && sel[1] == '1') && ws_bytes >= dd2_workspace_bytes(M, 1))
+            return dd2_run(coords, N, pair_i, pair_j, n_pairs, a, b, c, spectrum, M, ws, ws_bytes, d->tw4096, d->n_sm, st);
+    }
     if (dd_stream_supported(M, n_pairs) && ws_bytes >= dd_stream_workspace_bytes(M, n_pairs))
         return dd_stream_run(coords, N, pair_i, pair_j, n_pairs, a, b, c, spectrum, M, ws, ws_bytes, d->tw4096, st);
     if (dd_cols_supported(M)) {

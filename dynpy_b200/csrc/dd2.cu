@@ -1,0 +1,115 @@
+// Host side of the dipolar fast path: fused generator + column kernel (dd_cols2.cuh) and the
+// accumulate-power row kernel (fft_rows2.cuh), batched through the T workspace.
+#include "dd_cols2.cuh"
+#include "fft_rows2.cuh"
+#include "kernels.h"
+
+namespace dynpy {
+
+static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
+
+bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096 * 64; }
+
+// workspace: R[M] | TWT[M] | rsum[2*cap] | T[cap][11][M]
+i64 dd2_workspace_bytes(i64 M, i64 items) {
+    if (items < 1) items = 1;
+    return 2 * M * (i64)sizeof(cd) + align_up2(items * 16, 256) + items * DD_NSLOTS * M * (i64)sizeof(cd) + 256;
+}
+
+template <int M1>
+static cudaError_t launch_cols_dd2_M1(const ColsDD2Params& p, int n_sm, cudaStream_t st) {
+    auto kern = k_cols_dd2<M1>;
+    constexpr int R1 = M1 / 8, CW = 32 / R1;
+    const size_t smem = (size_t)4 * (M1 + M1 / 8) * CW * sizeof(cd) + 24 * 128 * sizeof(double) + 8 * 128 * sizeof(cd) + 2 * DD2_MAX_IDX * sizeof(int);  // + staging, twiddles, indices
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ProfScope prof(PROF_COLS, st);
+    kern<<<3 * n_sm, 128, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_cols_dd2(const ColsDD2Params& p, int n_sm, cudaStream_t st) {
+    switch ((int)(p.M >> 12)) {
+        case 16: return launch_cols_dd2_M1<16>(p, n_sm, st);
+        case 32: return launch_cols_dd2_M1<32>(p, n_sm, st);
+        case 64: return launch_cols_dd2_M1<64>(p, n_sm, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// rows of the slots listed in sel[0..nsel); `fix` selects the mean-removing instantiation
+cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int n_sm, cudaStream_t st) {
+    const size_t smem = (size_t)pad16(4096) * sizeof(cd);
+    p.nsel = nsel;
+    p.sel_pack = 0;
+    for (int s = 0; s < nsel; ++s) p.sel_pack |= (unsigned long long)sel[s] << (4 * s);
+    const i64 units = (i64)nsel * p.M1 * p.items;
+    if (units <= 0) return cudaSuccess;
+    int grid = 2 * n_sm;
+    if (grid > units) grid = (int)units;
+    ProfScope prof(PROF_ROWS, st);
+    cudaError_t e;
+    if (fix) {
+        e = cudaFuncSetAttribute(k_rows2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_rows2<true><<<grid, 256, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(k_rows2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_rows2<false><<<grid, 256, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
+            i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st) {
+    const i64 items_all = (P + 1) / 2;
+    const i64 fixed = 2 * M * (i64)sizeof(cd) + 256;
+    const i64 per_item = (i64)DD_NSLOTS * M * (i64)sizeof(cd) + 16;
+    i64 cap = (ws_bytes - fixed - 256) / per_item;
+    if (cap < 1) {
+        set_error("dipolar fast path: workspace too small (need >= %lld bytes)", (long long)dd2_workspace_bytes(M, 1));
+        return DYNPY_ERR_WORKSPACE;
+    }
+    if (cap > items_all) cap = items_all;
+    char* base = (char*)ws;
+    cd* R = (cd*)base;
+    cd* TWT = (cd*)(base + M * (i64)sizeof(cd));
+    double* rsum = (double*)(base + 2 * M * (i64)sizeof(cd));
+    cd* T = (cd*)(base + 2 * M * (i64)sizeof(cd) + align_up2(cap * 16, 256));
+
+    ColsDD2Params cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.X = X; cp.pi = pi; cp.pj = pj; cp.n_pairs = P; cp.N = N; cp.a = a; cp.b = b; cp.c = c;
+    cp.M = M; cp.inv_M = 1.0 / (double)M; cp.twp = tw; cp.rsum = rsum;
+    k_fill_twt<<<4 * n_sm, 256, 0, st>>>(TWT, (int)(M >> 12), M, 1.0 / (double)M);
+    DYNPY_CHECK(cudaGetLastError(), "dd twiddle table");
+    cp.twt = TWT;
+    // column transform of the all-ones series (for the mean removal of G_r)
+    cp.T = R; cp.items = 1; cp.ones = 1;
+    DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd ones columns");
+    cp.T = T; cp.ones = 0;
+
+    Rows2Params rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.T = T; rp.S = S; rp.M = M; rp.M1 = (int)(M >> 12); rp.nslots = DD_NSLOTS; rp.twp = tw;
+    const int acc_slot[DD_NSLOTS] = {0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6};
+    for (int s = 0; s < DD_NSLOTS; ++s) rp.acc_pack |= (unsigned long long)acc_slot[s] << (4 * s);
+    rp.R = R; rp.rsum = rsum; rp.fix_slot = 5; rp.inv_n = 1.0 / (double)N;
+
+    for (i64 it0 = 0; it0 < items_all; it0 += cap) {
+        const i64 cnt = items_all - it0 < cap ? items_all - it0 : cap;
+        DYNPY_CHECK(cudaMemsetAsync(rsum, 0, sizeof(double) * 2 * cnt, st), "dd rsum");
+        cp.pair0 = 2 * it0;
+        cp.items = cnt;
+        DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd columns");
+        rp.items = cnt;
+        const int plain[10] = {0, 1, 2, 3, 4, 6, 7, 8, 9, 10};
+        const int gr[1] = {5};
+        DYNPY_CHECK(launch_rows2(rp, plain, 10, false, n_sm, st), "dd rows");
+        DYNPY_CHECK(launch_rows2(rp, gr, 1, true, n_sm, st), "dd rows (G_r)");
+    }
+    return DYNPY_OK;
+}
+
+}  // namespace dynpy

@@ -2,9 +2,13 @@
 // grids in multiples of the SM count, and loops batches through the T workspace.
 #pragma once
 #include "fft_engine.cuh"
+#include "fft_rows2.cuh"
 #include "common.h"
 
 namespace dynpy {
+
+// defined in dd2.cu
+cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int n_sm, cudaStream_t st);
 
 template <int L, bool TWO_PASS, class Loader, int MODE>
 static cudaError_t launch_rows_L(const Loader& ld, const EpiParams& ep, const cd* tw, i64 f0, i64 f1, int gy,
@@ -111,9 +115,21 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
         int ys = ceil_div_i(target, (i64)M1 * nslots);
         if (ys > it1 - it0) ys = (int)(it1 - it0);
         if (ys < 1) ys = 1;
-        TLoader tl;
-        tl.T = T; tl.M1 = M1; tl.f_base = f0;
-        e = launch_rows_L<DYNPY_ROW_LEN, true, TLoader, MODE>(tl, ep, tw, f0, f1, ys * nslots, M1, st);
+        if constexpr (MODE == EPI_ACC_POWER) {
+            // accumulate-power rows: the balanced register-accumulating kernel of fft_rows2.cuh
+            if (nb % nslots != 0) return cudaErrorInvalidValue;
+            Rows2Params rp;
+            memset(&rp, 0, sizeof(rp));
+            rp.T = T; rp.S = ep.out; rp.M = M; rp.M1 = M1; rp.nslots = nslots; rp.items = nb / nslots;
+            rp.acc_pack = ep.acc_pack; rp.twp = tw;
+            int sel[16];
+            for (int s = 0; s < nslots; ++s) sel[s] = s;
+            e = launch_rows2(rp, sel, nslots, false, n_sm, st);
+        } else {
+            TLoader tl;
+            tl.T = T; tl.M1 = M1; tl.f_base = f0;
+            e = launch_rows_L<DYNPY_ROW_LEN, true, TLoader, MODE>(tl, ep, tw, f0, f1, ys * nslots, M1, st);
+        }
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

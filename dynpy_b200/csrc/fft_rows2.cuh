@@ -1,0 +1,171 @@
+// dynpy_b200 — second-pass (row) kernel of the four-step transform, accumulate-power flavour.
+//
+// One work unit = one row of 4096 complex points T[fft][k1][0..4096) (written by a column
+// kernel, inter-pass twiddle already applied).  The unit list is ordered (slot, k1, item) and cut
+// into equal contiguous ranges, one per CTA, so every CTA of the grid (2 per SM) carries the same
+// load and stays on one accumulator row for long stretches: |X|^2 is summed in registers and
+// flushed (coalesced fp64 REDs) only when (slot, k1) changes.
+//
+// Row transform 4096 = 16 x 16 x 16, decimation in frequency, 16 points per thread:
+//   step 1  thread t: x[t + 256 q] -> fft16 -> times W_256^{(t/16) k}   (half-warp-uniform table look-ups;
+//           the other factor W_4096^{(t%16) k} of the step twiddle commutes with step 2 and is merged into
+//           its twiddle) -> shared memory
+//   step 2  thread (h = t/16, m = t%16): fft16 over q' -> times W_4096^{m (h + 16 k2)} (one chain of
+//           complex products from two table entries) -> shared memory (same half warp reads it back)
+//   step 3  fft16 -> |X|^2 += into 16 registers; X index = t/16 + 16 (t%16) + 256 j.
+// The next row is pulled into L2 by one bulk prefetch while the current row is transformed.
+// fp64 instructions per point: 3*148/16 (codelets) + 4*15/16 + 4 + 4*15/16 + 2 = 41.3.
+#pragma once
+#include "codelets.cuh"
+#include "fft_engine.cuh"
+
+namespace dynpy {
+
+// Layout of one transform of the intermediate T (cd units): columns n2 are grouped in tiles of
+// DYNPY_T_TILE, addr(k1, n2) = ((n2 / TILE) * M1 + k1) * TILE + n2 % TILE.  The column kernel then writes
+// all k1 of its columns into one compact M1*TILE block (DRAM-page friendly) and a row is a sequence
+// of TILE-sized (1 KB) chunks.
+#ifndef DYNPY_T_TILE
+#define DYNPY_T_TILE 4096  // 4096: plain [k1][n2] rows (a 64-column tiling measured no gain on B200)
+#endif
+
+struct Rows2Params {
+    const cd* T;            // [items][nslots][M1][4096]
+    double* S;              // [nacc][M] accumulated |X|^2, internal order k1*4096 + k2
+    i64 M;
+    int M1;
+    int nslots;
+    i64 items;
+    unsigned long long acc_pack;  // 4-bit accumulator id per slot
+    int nsel;                     // slots handled by this launch ...
+    unsigned long long sel_pack;  // ... and their ids, 4 bits each
+    const cd* twp;          // W_4096^j
+    // optional mean removal of one slot:  x <- x - (mu_re + i mu_im) * R,  mu = rsum[2 item (+1)] * inv_n
+    const cd* R;            // [M1][4096] column transform of the all-ones series (nullptr: off)
+    const double* rsum;     // [2 * items]
+    int fix_slot;
+    double inv_n;
+};
+
+__device__ __forceinline__ cd ldcg_cd2(const cd* p) {
+    double2 r;
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+template <bool FIX>
+__global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
+    extern __shared__ double2 smem[];
+    const int tid = threadIdx.x;
+    const i64 units = (i64)p.nsel * p.M1 * p.items;
+    const i64 u0 = units * blockIdx.x / gridDim.x;
+    const i64 u1 = units * (blockIdx.x + 1) / gridDim.x;
+    if (u0 >= u1) return;
+
+    const int h = tid >> 4, m = tid & 15;
+    // step-2 merged twiddle chain: c0 = W_4096^{m h}, step = W_256^m
+    const cd c0 = ldg_cd(p.twp + m * h);
+    const cd cs = ldg_cd(p.twp + 16 * m);
+    const cd* tw1 = p.twp;  // W_256^{h k} = twp[16 h k]
+
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+
+    auto row_ptr = [&](i64 u, int& slot, int& k1, i64& item) -> const cd* {
+        const i64 sk = u / p.items;
+        item = u - sk * p.items;
+        const int si = (int)(sk / p.M1);
+        k1 = (int)(sk - (i64)si * p.M1);
+        slot = (int)((p.sel_pack >> (4 * si)) & 15ull);
+        return p.T + ((item * p.nslots + slot) * p.M1 << 12) + (i64)k1 * DYNPY_T_TILE;  // start of row k1 in tile 0
+    };
+    auto flush = [&](int slot, int k1) {
+        double* sr = reinterpret_cast<double*>(smem);
+        const int kk0 = h + 16 * m;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sr[kk0 + 256 * j] = acc[j];
+        __syncthreads();
+        double* dst = p.S + (i64)((p.acc_pack >> (4 * slot)) & 15ull) * p.M + ((i64)k1 << 12);
+        for (int k = tid; k < 4096; k += 256) atomicAdd(dst + k, sr[k]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    };
+
+    // element n2 = tid + 256 q of a row: tile (tid / TILE) + (256 / TILE) q, offset tid % TILE
+    auto t_off = [&](int q) -> i64 {
+        const int n2 = tid + 256 * q;
+        return (i64)(n2 / DYNPY_T_TILE) * p.M1 * DYNPY_T_TILE + (n2 % DYNPY_T_TILE);
+    };
+    int slot, k1;
+    i64 item;
+    const cd* src = row_ptr(u0, slot, k1, item);
+
+    cd nx[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
+
+    for (i64 u = u0; u < u1; ++u) {
+        cd v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = nx[q];
+        if constexpr (FIX) {
+            const double mr = p.rsum[2 * item] * p.inv_n, mi = p.rsum[2 * item + 1] * p.inv_n;
+            const cd* rr = p.R + (i64)k1 * DYNPY_T_TILE;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cd r = ldg_cd(rr + t_off(q));
+                v[q].x -= fma(mr, r.x, -(mi * r.y));
+                v[q].y -= fma(mr, r.y, mi * r.x);
+            }
+        }
+        // ---- step 1
+        fft16(v);
+        smem[pad16(tid)] = v[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) smem[pad16(k * 256 + tid)] = cmul(v[k], ldg_cd(tw1 + 16 * h * k));
+        __syncthreads();
+        // next row: decode now (its registers are loaded under step 3); the row after it is pulled into
+        // L2 by one bulk prefetch per chunk (DRAM latency under this load is several microseconds)
+        int nslot = slot, nk1 = k1;
+        i64 nitem = item;
+        if (u + 1 < u1) src = row_ptr(u + 1, nslot, nk1, nitem);
+        if (u + 2 < u1 && tid < 4096 / DYNPY_T_TILE) {
+            int s2, k2;
+            i64 i2;
+            const cd* pf = row_ptr(u + 2, s2, k2, i2);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf + (i64)tid * p.M1 * DYNPY_T_TILE),
+                         "r"(DYNPY_T_TILE * 16) : "memory");
+        }
+        // ---- step 2
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = smem[pad16(h * 256 + q * 16 + m)];
+        fft16(v);
+        {
+            cd w = c0;
+            asm volatile("" : "+d"(w.x), "+d"(w.y));  // keep the chain inside the loop (15 hoisted values would spill)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                smem[pad16(h * 256 + k * 16 + m)] = cmul(v[k], w);
+                if (k < 15) w = cmul(w, cs);
+            }
+        }
+        __syncwarp();
+        // ---- step 3
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = smem[pad16(tid * 16 + q)];
+        __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten
+        // next row (already on its way to L2) -> registers, under the last codelet; unconditional so that
+        // nx is dead during steps 1 and 2 (the last iteration re-reads its own row)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
+        fft16(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc[j]));
+        if (u + 1 == u1 || nslot != slot || nk1 != k1) flush(slot, k1);
+        slot = nslot; k1 = nk1; item = nitem;
+    }
+}
+
+}  // namespace dynpy

@@ -42,6 +42,12 @@ i64 dd_stream_workspace_bytes(i64 M, i64 n_pairs);
 int dd_stream_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c,
                   double* S, i64 M, void* ws, i64 ws_bytes, const cd* tw, cudaStream_t st);
 
+// dipolar fast path (dd2.cu): warp-autonomous fused column kernel + row kernel v2
+bool dd2_supported(i64 M);
+i64 dd2_workspace_bytes(i64 M, i64 items);
+int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
+            i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st);
+
 bool dd_cols_supported(i64 M);
 cudaError_t launch_cols_dd(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs, i64 items,
                            double a, double b, double c, cd* T, i64 M, double* rsum, const cd* tw, int n_sm,
