@@ -81,8 +81,8 @@ static inline i64 align_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
 static inline bool pow2(i64 m) { return m > 0 && (m & (m - 1)) == 0; }
 
 static int check_M(i64 M, i64 n) {
-    if (!pow2(M) || M < 32 || M > ((i64)1 << 24)) {
-        set_error("transform length M=%lld must be a power of two in [32, 2^24]", (long long)M);
+    if (!fft_length_ok(M)) {
+        set_error("transform length M=%lld must be a power of two in [32, 2^24] or 204800", (long long)M);
         return DYNPY_ERR_INVALID;
     }
     if (n < 1 || 2 * n - 1 > M) {
@@ -137,6 +137,8 @@ int dynpy_profile_read(double* ms_host, int64_t* launches_host) {
 int64_t dynpy_fft_length(int64_t n) {
     int64_t m = 32;
     while (m < 2 * n) m <<= 1;
+    // 50 x 4096 = 204800 >= 2n - 1 covers 65536 < n <= 102400 with 22 % fewer points than 2^18
+    if (m == ((int64_t)1 << 18) && 2 * n - 1 <= 50 * (int64_t)DYNPY_ROW_LEN) m = 50 * (int64_t)DYNPY_ROW_LEN;
     return m;
 }
 
@@ -202,7 +204,7 @@ int dynpy_wk_acf_sum_f64(const double* re, const double* im, int64_t n_series, i
 int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf, int64_t n_out, double scale,
                        void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!pow2(M) || M < 32 || M > ((i64)1 << 24) || n_acc < 1 || n_out < 1 || n_out > M || !spectrum || !acf) {
+    if (!fft_length_ok(M) || n_acc < 1 || n_out < 1 || n_out > M || !spectrum || !acf) {
         set_error("dynpy_ifft_acf_f64: invalid arguments");
         return DYNPY_ERR_INVALID;
     }

@@ -8,7 +8,7 @@ namespace dynpy {
 
 static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
 
-bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096 * 64; }
+bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096 * 64 || M == 4096 * 50; }
 
 // workspace: R[M] | TWT[M] | rsum[2*cap] | T[cap][11][M]
 i64 dd2_workspace_bytes(i64 M, i64 items) {
@@ -19,8 +19,7 @@ i64 dd2_workspace_bytes(i64 M, i64 items) {
 template <int M1>
 static cudaError_t launch_cols_dd2_M1(const ColsDD2Params& p, int n_sm, cudaStream_t st) {
     auto kern = k_cols_dd2<M1>;
-    constexpr int R1 = M1 / 8, CW = 32 / R1;
-    const size_t smem = (size_t)4 * (M1 + M1 / 8) * CW * sizeof(cd) + 24 * 128 * sizeof(double) + 8 * 128 * sizeof(cd) + 2 * DD2_MAX_IDX * sizeof(int);  // + staging, twiddles, indices
+    const size_t smem = ColShape<M1>::smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ProfScope prof(PROF_COLS, st);
@@ -33,13 +32,14 @@ static cudaError_t launch_cols_dd2(const ColsDD2Params& p, int n_sm, cudaStream_
         case 16: return launch_cols_dd2_M1<16>(p, n_sm, st);
         case 32: return launch_cols_dd2_M1<32>(p, n_sm, st);
         case 64: return launch_cols_dd2_M1<64>(p, n_sm, st);
+        case 50: return launch_cols_dd2_M1<50>(p, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // rows of the slots listed in sel[0..nsel); `fix` selects the mean-removing instantiation
 cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int n_sm, cudaStream_t st) {
-    const size_t smem = (size_t)pad16(4096) * sizeof(cd);
+    const size_t smem = (size_t)(pad16(4096) + 256) * sizeof(cd);  // row buffer + step-1 twiddle table
     p.nsel = nsel;
     p.sel_pack = 0;
     for (int s = 0; s < nsel; ++s) p.sel_pack |= (unsigned long long)sel[s] << (4 * s);

@@ -5,7 +5,7 @@
 // the zero-padded forward FFT of wiener_khinchin (ddrax.py:276-285) for all 11 real series of a
 // pair: nothing but the four-step intermediate T is written.
 //
-// Decomposition M = M1 x 4096, M1 = 8 R1 in {16, 32, 64}; sample n = 4096 n1 + n2.
+// Decomposition M = M1 x 4096, M1 = 8 R1 in {16, 32, 64} or M1 = 50; sample n = 4096 n1 + n2.
 //   * a WARP owns CW = 32/R1 adjacent columns n2 (R1 threads per column, 8 points per thread);
 //     the only data exchange of the M1-point column transform is inside the warp (4.5 KB of
 //     shared memory per warp, __syncwarp), there is no CTA-wide barrier in the kernel;
@@ -18,6 +18,10 @@
 //   * the work list (item, 16-column tile) is cut into equal contiguous ranges per CTA, item-major, so
 //     the whole grid writes into the T blocks of the same few items at any time (TLB reach); the
 //     inter-pass twiddles of a tile are 8 table look-ups per thread (table filled once per call).
+// M1 = 50 (M = 204800, the length used for 65536 < N <= 102400 frames): 5 threads per column, 6 columns
+// per warp (30 lanes), 5 frames per thread; radix-2 DIF split into the even (x) and odd (x W_50^n1)
+// 25-point transforms, each 5 x 5: fft5 over q (n1 = 5 q + m), twiddle W_25^{m a1}, exchange, fft5
+// over m; outputs k1 = 2 (a1 + 5 a2) + parity, 10 per thread.
 // The mean of r^-3 (G_r is the ACF of r^-3 - <r^-3>, ddrax.py:292) is NOT subtracted here: the
 // per-pair sums go to rsum[] and the row kernel subtracts mean x (column transform of the
 // all-ones series), which is linear and exact; `ones` mode produces that table.
@@ -56,30 +60,62 @@ template <> struct HalfCodelet<8> { static __device__ __forceinline__ void run(c
 
 __device__ __forceinline__ void cp_async8_(double* smem_dst, const double* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");  // 8-byte copies exist only as .ca
 }
+
+// compile-time shape of the column kernel for a given M1
+template <int M1> struct ColShape {
+    static constexpr bool MR = (M1 == 50);          // mixed radix 2 x 5 x 5
+    static constexpr int TPC = MR ? 5 : M1 / 8;     // threads per column
+    static constexpr int CW = MR ? 6 : 32 / TPC;    // columns per warp
+    static constexpr int NFR = MR ? 5 : 4;          // frames (non-zero samples) per thread
+    static constexpr int NTW = MR ? 10 : 8;         // outputs == inter-pass twiddles per thread
+    static constexpr int NWARP = 4;                 // warps per CTA; the CTA owns NWARP*CW adjacent columns
+    static constexpr int TCOLS = CW * NWARP;
+    static constexpr int NTILE = (4096 + TCOLS - 1) / TCOLS;
+    static constexpr int WSLOTS = MR ? 2 * 25 * CW : (M1 + M1 / 8) * CW;  // exchange buffer of one warp (cd units)
+    static constexpr int NTW1 = MR ? 50 : 64;       // step-1 twiddle table entries
+    static constexpr size_t smem_bytes() {
+        return (size_t)NWARP * WSLOTS * sizeof(cd) + (size_t)NFR * 6 * 128 * sizeof(double) + (size_t)NTW * 128 * sizeof(cd) +
+               2 * DD2_MAX_IDX * sizeof(int) + NTW1 * sizeof(cd);
+    }
+};
 
 template <int M1>
 __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
-    constexpr int R1 = M1 / 8;         // threads per column == first radix
-    constexpr int CW = 32 / R1;        // columns per warp
-    constexpr int QH = R1 / 2;         // non-zero inputs of a step-1 butterfly
-    constexpr int NIT = 8 / R1;        // step-1 butterflies per thread
-    constexpr int NWARP = 4;           // warps per CTA: the CTA owns NWARP*CW adjacent columns
-    constexpr int NTILE = 4096 / (CW * NWARP);
-    constexpr int WSLOTS = (M1 + M1 / 8) * CW;  // exchange buffer of one warp (cd units)
+    typedef ColShape<M1> SH;
+    constexpr bool MR = SH::MR;
+    constexpr int R1 = SH::TPC, CW = SH::CW, NFR = SH::NFR, NTW = SH::NTW, NWARP = SH::NWARP, NTILE = SH::NTILE;
+    constexpr int WSLOTS = SH::WSLOTS;
+    constexpr int QH = MR ? 5 : R1 / 2;  // non-zero inputs of a step-1 butterfly
+    constexpr int NIT = MR ? 1 : 8 / R1; // step-1 butterflies per thread
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     const int c = lane % CW;
-    const int bb = lane / CW;
+    const int bb = lane / CW;            // MR: lanes 30, 31 get bb == 5 and stay idle
+    const bool lane_on = bb < R1;
     cd* sm = smem + wid * WSLOTS;
-    // thread-private staging of the NEXT pair's coordinates: value v of this thread at stage[v*128 + tid]
+    // thread-private staging of the NEXT pair's coordinates: value v of this thread at stage[v*128] ...
     double* stage = reinterpret_cast<double*>(smem + NWARP * WSLOTS) + threadIdx.x;
-    // ... of the next tile's inter-pass twiddles (8 per thread): stw[j*128 + tid] ...
-    cd* stw = smem + NWARP * WSLOTS + 12 * 128 + threadIdx.x;
-    // ... and the atom indices of the pairs this CTA will visit (filled once)
-    int* sidx = reinterpret_cast<int*>(smem + NWARP * WSLOTS + 12 * 128 + 8 * 128);
+    // ... of the next tile's inter-pass twiddles: stw[j*128] ...
+    cd* stw = smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + threadIdx.x;
+    // ... the atom indices of the pairs this CTA will visit (filled once) ...
+    int* sidx = reinterpret_cast<int*>(smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + NTW * 128);
+    // ... and the step-1 twiddles: W_M1^{m k} as [k][m] (pow2), or W_25^{m a1} as [a1][m] then W_50^{5q+m} as [q][m]
+    cd* stw1 = smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + NTW * 128 + (2 * DD2_MAX_IDX * (int)sizeof(int)) / (int)sizeof(cd);
+    if constexpr (MR) {
+        if (threadIdx.x < 25) {
+            const int a = threadIdx.x / 5, m = threadIdx.x % 5;
+            double sn, cs;
+            sincospi(2.0 * (double)((m * a) % 25) / 25.0, &sn, &cs);
+            stw1[threadIdx.x] = make_double2(cs, -sn);
+            sincospi(2.0 * (double)(5 * a + m) / 50.0, &sn, &cs);
+            stw1[25 + threadIdx.x] = make_double2(cs, -sn);
+        }
+    } else {
+        if (threadIdx.x < 64) stw1[threadIdx.x] = ldg_cd(p.twp + (4096 / M1) * (threadIdx.x & 7) * (threadIdx.x >> 3));
+    }
     auto slot_of = [&](int row) { return (row + (row >> 3)) * CW + c; };
 
     const int items = p.ones ? 1 : (int)p.items;
@@ -91,47 +127,81 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
     const double KF = 1.5853309190424043;
 
-    int cur_tile = -1;
     int n2 = 0;
-    cd tw[8];
-    // frames of this thread: n1 = 8 q + bb + R1 it  (q < QH, it < NIT), fs = it*QH + q
-    auto frame_of = [&](int fs, int col) -> int { return (((fs % QH) * 8 + bb + (fs / QH) * R1) << 12) + col; };
-    // one series of the current (item, slot): 4 samples per thread -> column transform -> T
-    auto emit = [&](const cd (&smp)[4], cd* dst) {
+    bool on = false;  // this thread owns a real column (lane in use and n2 < 4096)
+    cd tw[NTW];
+    // n1 of this thread's fs-th frame, and k1 of its j-th output
+    auto n1_of = [&](int fs) -> int { return MR ? 5 * fs + bb : (fs % QH) * 8 + bb + (fs / QH) * R1; };
+    auto k1_of = [&](int j) -> int { return MR ? 2 * (bb + 5 * (j % 5)) + j / 5 : bb + R1 * j; };
+    auto col_of = [&](int tile) -> int { return (tile * NWARP + wid) * CW + c; };
+    // one series of the current (item, slot): NFR samples per thread -> column transform -> T
+    auto emit = [&](const cd (&smp)[NFR], cd* dst) {
+        if constexpr (MR) {
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int m = bb + it * R1;
-            cd u[R1];
+            for (int par = 0; par < 2; ++par) {
+                cd u[5];
 #pragma unroll
-            for (int q = 0; q < R1; ++q) u[q] = (q < QH) ? smp[it * QH + q] : make_double2(0.0, 0.0);
-            HalfCodelet<R1>::run(u);
-            sm[slot_of(m)] = u[0];
+                for (int q = 0; q < 5; ++q) u[q] = par ? cmul(smp[q], stw1[25 + 5 * q + (lane_on ? bb : 0)]) : smp[q];
+                fft5(u);
+                if (lane_on) {
+                    sm[(par * 25 + bb) * CW + c] = u[0];
 #pragma unroll
-            for (int k = 1; k < R1; ++k) sm[slot_of(k * 8 + m)] = cmul(u[k], ldg_cd(p.twp + (4096 / M1) * m * k));
+                    for (int a = 1; a < 5; ++a) sm[(par * 25 + a * 5 + bb) * CW + c] = cmul(u[a], stw1[5 * a + bb]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                cd v[5];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) v[m] = lane_on ? sm[(par * 25 + bb * 5 + m) * CW + c] : make_double2(0.0, 0.0);
+                fft5(v);
+                if (on) {
+#pragma unroll
+                    for (int a2 = 0; a2 < 5; ++a2)
+                        dst[(2 * (bb + 5 * a2) + par) * DYNPY_T_TILE] = cmul(v[a2], tw[par * 5 + a2]);
+                }
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int m = bb + it * R1;
+                cd u[R1];
+#pragma unroll
+                for (int q = 0; q < R1; ++q) u[q] = (q < QH) ? smp[it * QH + q] : make_double2(0.0, 0.0);
+                HalfCodelet<R1>::run(u);
+                sm[slot_of(m)] = u[0];
+#pragma unroll
+                for (int k = 1; k < R1; ++k) sm[slot_of(k * 8 + m)] = cmul(u[k], stw1[k * 8 + m]);
+            }
+            __syncwarp();
+            cd u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u[q] = sm[slot_of(bb * 8 + q)];
+            __syncwarp();
+            fft8(u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[(bb + R1 * j) * DYNPY_T_TILE] = cmul(u[j], tw[j]);
         }
-        __syncwarp();
-        cd u[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) u[q] = sm[slot_of(bb * 8 + q)];
-        __syncwarp();
-        fft8(u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[(bb + R1 * j) * DYNPY_T_TILE] = cmul(u[j], tw[j]);
     };
     auto set_tile = [&](int tile, bool staged) {
-        cur_tile = tile;
-        n2 = (tile * NWARP + wid) * CW + c;
+        n2 = col_of(tile);
+        on = lane_on && n2 < 4096;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tw[j] = staged ? stw[j * 128] : ldg_cd(p.twt + ((bb + R1 * j) << 12) + n2);
+        for (int j = 0; j < NTW; ++j)
+            tw[j] = staged ? stw[j * 128] : (on ? ldg_cd(p.twt + ((i64)k1_of(j) << 12) + n2) : make_double2(0.0, 0.0));
     };
+    auto t_off = [&]() -> i64 { return (i64)(n2 / DYNPY_T_TILE) * M1 * DYNPY_T_TILE + n2 % DYNPY_T_TILE; };
+    __syncthreads();  // stw1 is filled
 
     if (p.ones) {
         for (int w = w0; w < w1; ++w) {
             set_tile(w % NTILE, false);
-            cd smp[4];
+            cd smp[NFR];
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) smp[fs] = make_double2(frame_of(fs, n2) < nfr ? 1.0 : 0.0, 0.0);
-            emit(smp, p.T + (i64)(n2 / DYNPY_T_TILE) * M1 * DYNPY_T_TILE + n2 % DYNPY_T_TILE);
+            for (int fs = 0; fs < NFR; ++fs) smp[fs] = make_double2(on && (n1_of(fs) << 12) + n2 < nfr ? 1.0 : 0.0, 0.0);
+            emit(smp, p.T + t_off());
         }
         return;
     }
@@ -143,13 +213,11 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     // are evicted from L2 by the T stream; a dependent global look-up per pair costs microseconds)
     const int item_lo = w0 / NTILE, item_hi = (w1 - 1) / NTILE;
     const int n_idx = 2 * (item_hi - item_lo + 1);
-    for (int k = threadIdx.x; k < n_idx; k += blockDim.x) {
+    for (int k = threadIdx.x; k < n_idx && k < DD2_MAX_IDX; k += blockDim.x) {
         const i64 pr = p.pair0 + 2 * (i64)item_lo + k;
-        const bool ok = pr < p.n_pairs && k < DD2_MAX_IDX;
-        if (k < DD2_MAX_IDX) {
-            sidx[2 * k] = ok ? __ldg(p.pi + pr) : -1;
-            sidx[2 * k + 1] = ok ? __ldg(p.pj + pr) : -1;
-        }
+        const bool ok = pr < p.n_pairs;
+        sidx[2 * k] = ok ? __ldg(p.pi + pr) : -1;
+        sidx[2 * k + 1] = ok ? __ldg(p.pj + pr) : -1;
     }
     __syncthreads();
     auto atoms_of = [&](int s, int& ai, int& aj) {
@@ -164,28 +232,30 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
         }
     };
     auto stage_step = [&](int s, int ai, int aj) {
-        if (s < S && ai >= 0) {
-            const int col = (((w0 + (s >> 1)) % NTILE) * NWARP + wid) * CW + c;
-            const double* xi = p.X + (i64)ai * 3 * p.N;
-            const double* xj = p.X + (i64)aj * 3 * p.N;
+        if (s < S) {
+            const int col = col_of((w0 + (s >> 1)) % NTILE);
+            const bool col_on = lane_on && col < 4096;
+            if (ai >= 0 && col_on) {
+                const double* xi = p.X + (i64)ai * 3 * p.N;
+                const double* xj = p.X + (i64)aj * 3 * p.N;
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) {
-                const int fr = frame_of(fs, col);
-                if (fr < nfr) {
+                for (int fs = 0; fs < NFR; ++fs) {
+                    const int fr = (n1_of(fs) << 12) + col;
+                    if (fr < nfr) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        cp_async8_(stage + (fs * 6 + d) * 128, xi + d * p.N + fr);
-                        cp_async8_(stage + (fs * 6 + 3 + d) * 128, xj + d * p.N + fr);
+                        for (int d = 0; d < 3; ++d) {
+                            cp_async8_(stage + (fs * 6 + d) * 128, xi + d * p.N + fr);
+                            cp_async8_(stage + (fs * 6 + 3 + d) * 128, xj + d * p.N + fr);
+                        }
                     }
                 }
             }
-        }
-        if (s < S && (s & 1) == 0) {  // first pair of a unit: its tile's inter-pass twiddles
-            const int col = (((w0 + (s >> 1)) % NTILE) * NWARP + wid) * CW + c;
+            if ((s & 1) == 0 && col_on) {  // first pair of a unit: its tile's inter-pass twiddles
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(stw + j * 128);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p.twt + ((bb + R1 * j) << 12) + col) : "memory");
+                for (int j = 0; j < NTW; ++j) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(stw + j * 128);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p.twt + ((i64)k1_of(j) << 12) + col) : "memory");
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -195,7 +265,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     stage_step(0, ai, aj);
     atoms_of(1, ai_n, aj_n);
 
-    double y20p[4], r3p[4];
+    double y20p[NFR], r3p[NFR];
     for (int s = 0; s < S; ++s) {
         const int unit = w0 + (s >> 1);
         const int item = unit / NTILE;  // item-major: the whole grid works on the same few items at any time,
@@ -203,14 +273,14 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
         const int hq = s & 1;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (hq == 0) set_tile(tile, true);
-        cd* tbase = p.T + (i64)item * 11 * p.M + (i64)(n2 / DYNPY_T_TILE) * M1 * DYNPY_T_TILE + n2 % DYNPY_T_TILE;
-        const bool exists = ai >= 0;
-        double gx[4], gy[4], gz[4], g3[4];
+        cd* tbase = p.T + (i64)item * 11 * p.M + t_off();
+        const bool exists = ai >= 0 && on;
+        double gx[NFR], gy[NFR], gz[NFR], g3[NFR];
         {
             double rs = 0.0;
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) {
-                const bool ok = exists && frame_of(fs, n2) < nfr;
+            for (int fs = 0; fs < NFR; ++fs) {
+                const bool ok = exists && (n1_of(fs) << 12) + n2 < nfr;
                 double v[6];
 #pragma unroll
                 for (int d = 0; d < 6; ++d) v[d] = ok ? stage[(fs * 6 + d) * 128] : (d < 3 ? 0.0 : 1.0);
@@ -227,57 +297,58 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
                 rs += g3[fs];
             }
             // the staging slots are free again: next step's coordinates, and the atoms of the one after
+            const bool pair_exists = ai >= 0;
             ai = ai_n; aj = aj_n;
             stage_step(s + 1, ai, aj);
             atoms_of(s + 2, ai_n, aj_n);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, o);
-            if (lane == 0 && exists) atomicAdd(p.rsum + 2 * item + hq, rs);
+            if (lane == 0 && pair_exists) atomicAdd(p.rsum + 2 * item + hq, rs);
         }
-        cd smp[4];
+        cd smp[NFR];
 #pragma unroll
-        for (int fs = 0; fs < 4; ++fs) {
+        for (int fs = 0; fs < NFR; ++fs) {
             const double k = C21 * gz[fs];
             smp[fs] = make_double2(k * gx[fs], k * gy[fs]);
         }
         emit(smp, tbase + (1 + hq) * p.M);
 #pragma unroll
-        for (int fs = 0; fs < 4; ++fs) {
+        for (int fs = 0; fs < NFR; ++fs) {
             const double k = (KF * C21) * g3[fs] * gz[fs];
             smp[fs] = make_double2(k * gx[fs], k * gy[fs]);
         }
         emit(smp, tbase + (7 + hq) * p.M);
 #pragma unroll
-        for (int fs = 0; fs < 4; ++fs)
+        for (int fs = 0; fs < NFR; ++fs)
             smp[fs] = make_double2(C22 * (gx[fs] * gx[fs] - gy[fs] * gy[fs]), (2.0 * C22) * gx[fs] * gy[fs]);
         emit(smp, tbase + (3 + hq) * p.M);
 #pragma unroll
-        for (int fs = 0; fs < 4; ++fs) {
+        for (int fs = 0; fs < NFR; ++fs) {
             const double k = KF * g3[fs];
             smp[fs] = make_double2(k * smp[fs].x, k * smp[fs].y);
         }
         emit(smp, tbase + (9 + hq) * p.M);
         if (hq == 0) {
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) {
-                const bool ok = exists && frame_of(fs, n2) < nfr;
+            for (int fs = 0; fs < NFR; ++fs) {
+                const bool ok = exists && (n1_of(fs) << 12) + n2 < nfr;
                 y20p[fs] = ok ? C20 * fma(3.0 * gz[fs], gz[fs], -1.0) : 0.0;
                 r3p[fs] = g3[fs];
             }
         } else {
-            double y20q[4];
+            double y20q[NFR];
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) {
-                const bool ok = exists && frame_of(fs, n2) < nfr;
+            for (int fs = 0; fs < NFR; ++fs) {
+                const bool ok = exists && (n1_of(fs) << 12) + n2 < nfr;
                 y20q[fs] = ok ? C20 * fma(3.0 * gz[fs], gz[fs], -1.0) : 0.0;
                 smp[fs] = make_double2(y20p[fs], y20q[fs]);
             }
             emit(smp, tbase);
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) smp[fs] = make_double2(KF * r3p[fs] * y20p[fs], KF * g3[fs] * y20q[fs]);
+            for (int fs = 0; fs < NFR; ++fs) smp[fs] = make_double2(KF * r3p[fs] * y20p[fs], KF * g3[fs] * y20q[fs]);
             emit(smp, tbase + 6 * p.M);
 #pragma unroll
-            for (int fs = 0; fs < 4; ++fs) smp[fs] = make_double2(r3p[fs], g3[fs]);
+            for (int fs = 0; fs < NFR; ++fs) smp[fs] = make_double2(r3p[fs], g3[fs]);
             emit(smp, tbase + 5 * p.M);
         }
     }

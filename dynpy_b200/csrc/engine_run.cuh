@@ -59,9 +59,17 @@ static cudaError_t launch_cols_M1(const Loader& ld, cd* T, const cd* tw, i64 M, 
 }
 
 template <class Loader>
+static cudaError_t launch_cols50(const Loader& ld, cd* T, i64 M, i64 f0, i64 f1, int gy, cudaStream_t st) {
+    ProfScope prof(PROF_COLS, st);
+    k_cols50<Loader><<<dim3(DYNPY_ROW_LEN / 128, gy), 128, 0, st>>>(ld, T, M, 1.0 / (double)M, f0, f1, gy);
+    return cudaGetLastError();
+}
+
+template <class Loader>
 static cudaError_t launch_cols(int M1, const Loader& ld, cd* T, const cd* tw, i64 M, i64 f0, i64 f1, int gy,
                                cudaStream_t st) {
     switch (M1) {
+        case 50: return launch_cols50<Loader>(ld, T, M, f0, f1, gy, st);
         case 2: return launch_cols_M1<2, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 4: return launch_cols_M1<4, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 8: return launch_cols_M1<8, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
@@ -88,7 +96,7 @@ template <class Loader, int MODE>
 static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft, i64 M, int nslots, cd* T,
                                i64 T_cap, const cd* tw, int n_sm, cudaStream_t st) {
     if (n_fft <= 0) return cudaSuccess;
-    if (M < 32 || (M & (M - 1)) || M > ((i64)1 << 24)) return cudaErrorInvalidValue;
+    if (!fft_length_ok(M)) return cudaErrorInvalidValue;
     const int target = 4 * n_sm;  // CTAs in flight we aim for (>= 2 waves at 2 CTA/SM)
     if (M <= DYNPY_ROW_LEN) {
         i64 items = (n_fft + nslots - 1) / nslots;
@@ -105,7 +113,7 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
         i64 f0 = it0 * nslots, f1 = it1 * nslots < n_fft ? it1 * nslots : n_fft;
         i64 nb = f1 - f0;
         // first pass: (4096/C) tiles x gy CTAs
-        int tiles = M1 <= 16 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / C
+        int tiles = M1 == 50 ? DYNPY_ROW_LEN / 128 : M1 <= 16 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / C
         int gy1 = ceil_div_i(target, tiles);
         if (gy1 > nb) gy1 = (int)nb;
         if (gy1 < 1) gy1 = 1;

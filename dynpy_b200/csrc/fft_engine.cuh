@@ -24,12 +24,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "codelets.cuh"
+
 namespace dynpy {
 
 typedef double2 cd;
 typedef long long i64;
 
 #define DYNPY_ROW_LEN 4096  // M2 of the two-pass split
+
+// transform lengths the engine implements: powers of two in [32, 2^24] and 50 * 4096
+static inline bool fft_length_ok(long long M) {
+    return (M >= 32 && M <= (1ll << 24) && (M & (M - 1)) == 0) || M == 50ll * DYNPY_ROW_LEN;
+}
 #ifndef DYNPY_ROWS_MINB
 #define DYNPY_ROWS_MINB 2   // resident CTAs per SM the row kernel is compiled for
 #endif
@@ -501,6 +508,41 @@ k_cols(Loader ld, cd* __restrict__ T, const cd* __restrict__ twp, i64 M, double 
 #pragma unroll
         for (int j = 0; j < RL; ++j) dst[(i64)(kk0 + j * kstride) * M2] = cmul(v[j], tw[j]);
         if constexpr (S >= 2) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- first pass, M1 = 50 (M = 204800)
+// Any loader, one thread per column n2: the 50-point column transform is a radix-2 DIF split into two
+// 25-point codelets (even k1: x[j] + x[j+25]; odd k1: (x[j] - x[j+25]) W_50^j), done one after the other
+// to stay inside the register file; the inter-pass twiddles W_M^{n2 k1} run as a chain per parity.
+// M = 204800 is the transform length for 65536 < N <= 102400 frames (22 % fewer points than 2^18).
+template <class Loader>
+__global__ void __launch_bounds__(128) k_cols50(Loader ld, cd* __restrict__ T, i64 M, double inv_M, i64 f_begin,
+                                                i64 f_end, int f_step) {
+    constexpr int M2 = DYNPY_ROW_LEN;
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const cd w1 = w_exact(n2, inv_M);          // W_M^{n2}
+    const cd w2 = w_exact(2 * (i64)n2, inv_M);  // W_M^{2 n2}
+    for (i64 f = f_begin + blockIdx.y; f < f_end; f += f_step) {
+        typename Loader::Ctx ctx = ld.begin(f);
+        cd* dst = T + ((f - f_begin) * 50) * (i64)M2 + n2;
+#pragma unroll 1
+        for (int par = 0; par < 2; ++par) {
+            cd v[25];
+#pragma unroll
+            for (int j = 0; j < 25; ++j) {
+                const cd a = ld.finish(ctx, ld.raw(ctx, (i64)j * M2 + n2));
+                const cd b = ld.finish(ctx, ld.raw(ctx, (i64)(j + 25) * M2 + n2));
+                v[j] = par ? csub(a, b) : cadd(a, b);
+            }
+            if (par) fft25_odd(v); else fft25(v);
+            cd w = par ? w1 : make_double2(1.0, 0.0);
+#pragma unroll
+            for (int a = 0; a < 25; ++a) {
+                dst[(i64)(2 * a + par) * M2] = cmul(v[a], w);
+                w = cmul(w, w2);
+            }
+        }
     }
 }
 

@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     // step-2 merged twiddle chain: c0 = W_4096^{m h}, step = W_256^m
     const cd c0 = ldg_cd(p.twp + m * h);
     const cd cs = ldg_cd(p.twp + 16 * m);
-    const cd* tw1 = p.twp;  // W_256^{h k} = twp[16 h k]
+    // step-1 twiddles W_256^{h k} = twp[16 h k] in shared memory, [k][h]: the two h of a warp are adjacent, so a
+    // look-up costs one wavefront (from global they miss the small L1 and stall on L2 latency)
+    cd* stw1 = smem + pad16(4096);
+    stw1[tid] = ldg_cd(p.twp + 16 * (tid & 15) * (tid >> 4));
+    __syncthreads();
 
     double acc[16];
 #pragma unroll
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         fft16(v);
         smem[pad16(tid)] = v[0];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) smem[pad16(k * 256 + tid)] = cmul(v[k], ldg_cd(tw1 + 16 * h * k));
+        for (int k = 1; k < 16; ++k) smem[pad16(k * 256 + tid)] = cmul(v[k], stw1[k * 16 + h]);
         __syncthreads();
         // next row: decode now (its registers are loaded under step 3); the row after it is pulled into
         // L2 by one bulk prefetch per chunk (DRAM latency under this load is several microseconds)

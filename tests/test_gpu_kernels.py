@@ -43,10 +43,25 @@ def test_wk_sum_complex_all_plans(ops, N):
     z *= np.exp(-np.arange(N) / (0.3 * N + 1))[None]
     spec = ops.wk_acf_sum(dev(z.real), dev(z.imag))
     M = spec.numel()
-    assert M == max(32, 1 << int(np.ceil(np.log2(2 * N))))
+    assert M == (204800 if 65536 < N <= 102400 else max(32, 1 << int(np.ceil(np.log2(2 * N)))))
     acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
     ref = sum(orc.wiener_khinchin(z[s]) for s in range(S))
     assert nerr(acf, ref) < 1e-12, nerr(acf, ref)
+
+
+@pytest.mark.parametrize("N", [65537, 80000, 102400])
+def test_wk_mixed_radix_length_matches_power_of_two(ops, N):
+    """M = 50 x 4096 (radix-5 column pass) and M = 2^18 give the same linear ACF (any M >= 2N-1 does)."""
+    rng = np.random.default_rng(N)
+    z = rng.normal(size=(4, N))
+    out = {}
+    for M in (204800, 1 << 18):
+        spec = ops.wk_acf_sum(dev(z), pack_real_pairs=True, M=M)
+        assert spec.numel() == M
+        out[M] = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
+    ref = sum(orc.wiener_khinchin(z[s]) for s in range(4))
+    assert nerr(out[204800], ref) < 1e-12
+    assert nerr(out[204800], out[1 << 18]) < 1e-12
 
 
 @pytest.mark.parametrize("N", [1 << 20, 3000000, 6000000])  # M1 = 512, 2048, 4096 (largest supported)

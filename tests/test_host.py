@@ -35,7 +35,9 @@ def test_library_exports_every_declared_symbol():
     assert lib.dynpy_version() >= 100
     # pure host helpers may be called without a GPU
     assert lib.dynpy_fft_length(316) == 1024
-    assert lib.dynpy_fft_length(100000) == 262144
+    assert lib.dynpy_fft_length(100000) == 204800  # 50 x 4096 covers 65536 < n <= 102400
+    assert lib.dynpy_fft_length(65536) == 131072
+    assert lib.dynpy_fft_length(102401) == 262144
     assert lib.dynpy_fft_length(1) == 32
     assert lib.dynpy_fft_workspace_bytes(4096, 10) == 0
     assert lib.dynpy_fft_workspace_bytes(8192, 3) == 3 * 8192 * 16

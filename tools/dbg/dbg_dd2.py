@@ -31,6 +31,14 @@ for mode, env in modes:
     G = ops.ifft_acf(spec, F, 1.0 / (M * F)).cpu().numpy()
     res[mode] = G
     print("mode", mode, "time %.4f s" % dt, "pf/s %.3e" % (P * F / dt), "words/cols/rows ms", [round(x, 2) for x in ms[:3]], list(ln[:3]))
+if F > 65536 and F <= 102400:
+    os.environ["DYNPY_DD_PATH"] = "v2"
+    M2 = 1 << 18
+    spec = ops.dd_pairs_to_spectrum(w, pi, pj, (L, L, L), M=M2)
+    Gp = ops.ifft_acf(spec, F, 1.0 / (M2 * F)).cpu().numpy()
+    for m in res:
+        err = [np.max(np.abs(res[m][c] - Gp[c])) / np.max(np.abs(Gp[c])) for c in range(7)]
+        print(m, "(M=%d) vs v2 at M=2^18, normwise err" % M, ["%.1e" % e for e in err])
 if len(res) < 2:
     sys.exit(0)
 err = [np.max(np.abs(res["v2"][c] - res["v1"][c])) / np.max(np.abs(res["v1"][c])) for c in range(7)]
