@@ -3,6 +3,7 @@
 #include "dd_cols2.cuh"
 #include "fft_rows2.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace dynpy {
 
@@ -10,10 +11,13 @@ static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
 
 bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096 * 64 || M == 4096 * 50; }
 
-// workspace: R[M] | TWT[M] | rsum[2*cap] | T[cap][11][M]
+// bytes of one padded transform of T
+static inline i64 t_bytes(i64 M) { return (M >> 12) * (i64)DYNPY_T_RS * (i64)sizeof(cd); }
+
+// workspace: R[M'] | TWT[M] | rsum[2*cap] | T[cap][11][M']   (M' = M1 * DYNPY_T_RS padded rows)
 i64 dd2_workspace_bytes(i64 M, i64 items) {
     if (items < 1) items = 1;
-    return 2 * M * (i64)sizeof(cd) + align_up2(items * 16, 256) + items * DD_NSLOTS * M * (i64)sizeof(cd) + 256;
+    return t_bytes(M) + M * (i64)sizeof(cd) + align_up2(items * 16, 256) + items * DD_NSLOTS * t_bytes(M) + 512;
 }
 
 template <int M1>
@@ -45,6 +49,11 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
     for (int s = 0; s < nsel; ++s) p.sel_pack |= (unsigned long long)sel[s] << (4 * s);
     const i64 units = (i64)nsel * p.M1 * p.items;
     if (units <= 0) return cudaSuccess;
+    {
+        static int pf = -1;
+        if (pf < 0) { const char* e = getenv("DYNPY_ROWS_PF"); pf = e ? atoi(e) : 2; }
+        p.pf_dist = pf;
+    }
     int grid = 2 * n_sm;
     if (grid > units) grid = (int)units;
     ProfScope prof(PROF_ROWS, st);
@@ -64,8 +73,8 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
 int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
             i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st) {
     const i64 items_all = (P + 1) / 2;
-    const i64 fixed = 2 * M * (i64)sizeof(cd) + 256;
-    const i64 per_item = (i64)DD_NSLOTS * M * (i64)sizeof(cd) + 16;
+    const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 512;
+    const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16;
     i64 cap = (ws_bytes - fixed - 256) / per_item;
     if (cap < 1) {
         set_error("dipolar fast path: workspace too small (need >= %lld bytes)", (long long)dd2_workspace_bytes(M, 1));
@@ -74,9 +83,9 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     if (cap > items_all) cap = items_all;
     char* base = (char*)ws;
     cd* R = (cd*)base;
-    cd* TWT = (cd*)(base + M * (i64)sizeof(cd));
-    double* rsum = (double*)(base + 2 * M * (i64)sizeof(cd));
-    cd* T = (cd*)(base + 2 * M * (i64)sizeof(cd) + align_up2(cap * 16, 256));
+    cd* TWT = (cd*)(base + t_bytes(M));
+    double* rsum = (double*)(base + t_bytes(M) + M * (i64)sizeof(cd));
+    cd* T = (cd*)(base + t_bytes(M) + M * (i64)sizeof(cd) + align_up2(cap * 16, 256));
 
     ColsDD2Params cp;
     memset(&cp, 0, sizeof(cp));
@@ -92,7 +101,7 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
 
     Rows2Params rp;
     memset(&rp, 0, sizeof(rp));
-    rp.T = T; rp.S = S; rp.M = M; rp.M1 = (int)(M >> 12); rp.nslots = DD_NSLOTS; rp.twp = tw;
+    rp.T = T; rp.S = S; rp.M = M; rp.M1 = (int)(M >> 12); rp.rs = DYNPY_T_RS; rp.nslots = DD_NSLOTS; rp.twp = tw;
     const int acc_slot[DD_NSLOTS] = {0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6};
     for (int s = 0; s < DD_NSLOTS; ++s) rp.acc_pack |= (unsigned long long)acc_slot[s] << (4 * s);
     rp.R = R; rp.rsum = rsum; rp.fix_slot = 5; rp.inv_n = 1.0 / (double)N;

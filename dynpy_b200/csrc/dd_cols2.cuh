@@ -29,7 +29,7 @@
 #include "codelets.cuh"
 #include "dd_device.cuh"
 #include "fft_engine.cuh"
-#include "fft_rows2.cuh"  // DYNPY_T_TILE: layout of T
+#include "fft_rows2.cuh"  // DYNPY_T_RS: layout of T
 
 namespace dynpy {
 
@@ -42,7 +42,7 @@ struct ColsDD2Params {
     i64 items;         // pair-pairs in the batch
     i64 N;
     double a, b, c;
-    cd* T;             // [items][11][M1][4096]   (ones mode: [M1][4096])
+    cd* T;             // [items][11][M1][DYNPY_T_RS]   (ones mode: [M1][DYNPY_T_RS])
     i64 M;
     double inv_M;
     double* rsum;      // [2 * items] sums of r^-3 (zeroed by the caller)
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     const int w0 = (int)((i64)units * blockIdx.x / gridDim.x), w1 = (int)((i64)units * (blockIdx.x + 1) / gridDim.x);
     if (w0 >= w1) return;
     const int nfr = (int)(p.N < (i64)M1 * 2048 ? p.N : (i64)M1 * 2048);  // frames beyond M/2 never exist
+    constexpr i64 TS = (i64)M1 * DYNPY_T_RS;  // one transform of T
 
     const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
     const double KF = 1.5853309190424043;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
                 if (on) {
 #pragma unroll
                     for (int a2 = 0; a2 < 5; ++a2)
-                        dst[(2 * (bb + 5 * a2) + par) * DYNPY_T_TILE] = cmul(v[a2], tw[par * 5 + a2]);
+                        dst[(2 * (bb + 5 * a2) + par) * DYNPY_T_RS] = cmul(v[a2], tw[par * 5 + a2]);
                 }
             }
             __syncwarp();
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
             __syncwarp();
             fft8(u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[(bb + R1 * j) * DYNPY_T_TILE] = cmul(u[j], tw[j]);
+            for (int j = 0; j < 8; ++j) dst[(bb + R1 * j) * DYNPY_T_RS] = cmul(u[j], tw[j]);
         }
     };
     auto set_tile = [&](int tile, bool staged) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
         for (int j = 0; j < NTW; ++j)
             tw[j] = staged ? stw[j * 128] : (on ? ldg_cd(p.twt + ((i64)k1_of(j) << 12) + n2) : make_double2(0.0, 0.0));
     };
-    auto t_off = [&]() -> i64 { return (i64)(n2 / DYNPY_T_TILE) * M1 * DYNPY_T_TILE + n2 % DYNPY_T_TILE; };
+    auto t_off = [&]() -> i64 { return n2; };
     __syncthreads();  // stw1 is filled
 
     if (p.ones) {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
         const int hq = s & 1;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (hq == 0) set_tile(tile, true);
-        cd* tbase = p.T + (i64)item * 11 * p.M + t_off();
+        cd* tbase = p.T + (i64)item * 11 * TS + t_off();
         const bool exists = ai >= 0 && on;
         double gx[NFR], gy[NFR], gz[NFR], g3[NFR];
         {
@@ -311,23 +312,23 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
             const double k = C21 * gz[fs];
             smp[fs] = make_double2(k * gx[fs], k * gy[fs]);
         }
-        emit(smp, tbase + (1 + hq) * p.M);
+        emit(smp, tbase + (1 + hq) * TS);
 #pragma unroll
         for (int fs = 0; fs < NFR; ++fs) {
             const double k = (KF * C21) * g3[fs] * gz[fs];
             smp[fs] = make_double2(k * gx[fs], k * gy[fs]);
         }
-        emit(smp, tbase + (7 + hq) * p.M);
+        emit(smp, tbase + (7 + hq) * TS);
 #pragma unroll
         for (int fs = 0; fs < NFR; ++fs)
             smp[fs] = make_double2(C22 * (gx[fs] * gx[fs] - gy[fs] * gy[fs]), (2.0 * C22) * gx[fs] * gy[fs]);
-        emit(smp, tbase + (3 + hq) * p.M);
+        emit(smp, tbase + (3 + hq) * TS);
 #pragma unroll
         for (int fs = 0; fs < NFR; ++fs) {
             const double k = KF * g3[fs];
             smp[fs] = make_double2(k * smp[fs].x, k * smp[fs].y);
         }
-        emit(smp, tbase + (9 + hq) * p.M);
+        emit(smp, tbase + (9 + hq) * TS);
         if (hq == 0) {
 #pragma unroll
             for (int fs = 0; fs < NFR; ++fs) {
@@ -346,10 +347,10 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
             emit(smp, tbase);
 #pragma unroll
             for (int fs = 0; fs < NFR; ++fs) smp[fs] = make_double2(KF * r3p[fs] * y20p[fs], KF * g3[fs] * y20q[fs]);
-            emit(smp, tbase + 6 * p.M);
+            emit(smp, tbase + 6 * TS);
 #pragma unroll
             for (int fs = 0; fs < NFR; ++fs) smp[fs] = make_double2(r3p[fs], g3[fs]);
-            emit(smp, tbase + 5 * p.M);
+            emit(smp, tbase + 5 * TS);
         }
     }
 }

@@ -128,7 +128,7 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
             if (nb % nslots != 0) return cudaErrorInvalidValue;
             Rows2Params rp;
             memset(&rp, 0, sizeof(rp));
-            rp.T = T; rp.S = ep.out; rp.M = M; rp.M1 = M1; rp.nslots = nslots; rp.items = nb / nslots;
+            rp.T = T; rp.S = ep.out; rp.M = M; rp.M1 = M1; rp.rs = DYNPY_ROW_LEN; rp.nslots = nslots; rp.items = nb / nslots;
             rp.acc_pack = ep.acc_pack; rp.twp = tw;
             int sel[16];
             for (int s = 0; s < nslots; ++s) sel[s] = s;

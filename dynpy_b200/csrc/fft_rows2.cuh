@@ -21,19 +21,19 @@
 
 namespace dynpy {
 
-// Layout of one transform of the intermediate T (cd units): columns n2 are grouped in tiles of
-// DYNPY_T_TILE, addr(k1, n2) = ((n2 / TILE) * M1 + k1) * TILE + n2 % TILE.  The column kernel then writes
-// all k1 of its columns into one compact M1*TILE block (DRAM-page friendly) and a row is a sequence
-// of TILE-sized (1 KB) chunks.
-#ifndef DYNPY_T_TILE
-#define DYNPY_T_TILE 4096  // 4096: plain [k1][n2] rows (a 64-column tiling measured no gain on B200)
+// Layout of the intermediate T: row k1 of transform t starts at (t * M1 + k1) * DYNPY_T_RS (cd units).  The
+// row stride is 4096 + a small pad so that the hundreds of rows streamed concurrently (one per CTA, all
+// a multiple of 64 KB apart otherwise) do not collide on the same HBM channels / banks.
+#ifndef DYNPY_T_RS
+#define DYNPY_T_RS (4096 + 16)
 #endif
 
 struct Rows2Params {
-    const cd* T;            // [items][nslots][M1][4096]
+    const cd* T;            // [items][nslots][M1][rs]
     double* S;              // [nacc][M] accumulated |X|^2, internal order k1*4096 + k2
     i64 M;
     int M1;
+    int rs;                 // row stride of T in cd units (4096, or DYNPY_T_RS for the padded layout)
     int nslots;
     i64 items;
     unsigned long long acc_pack;  // 4-bit accumulator id per slot
@@ -41,10 +41,11 @@ struct Rows2Params {
     unsigned long long sel_pack;  // ... and their ids, 4 bits each
     const cd* twp;          // W_4096^j
     // optional mean removal of one slot:  x <- x - (mu_re + i mu_im) * R,  mu = rsum[2 item (+1)] * inv_n
-    const cd* R;            // [M1][4096] column transform of the all-ones series (nullptr: off)
+    const cd* R;            // [M1][rs] column transform of the all-ones series (nullptr: off)
     const double* rsum;     // [2 * items]
     int fix_slot;
     double inv_n;
+    int pf_dist;            // rows of look-ahead of the L2 bulk prefetch (0: off)
 };
 
 __device__ __forceinline__ cd ldcg_cd2(const cd* p) {
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         const int si = (int)(sk / p.M1);
         k1 = (int)(sk - (i64)si * p.M1);
         slot = (int)((p.sel_pack >> (4 * si)) & 15ull);
-        return p.T + ((item * p.nslots + slot) * p.M1 << 12) + (i64)k1 * DYNPY_T_TILE;  // start of row k1 in tile 0
+        return p.T + ((item * p.nslots + slot) * p.M1 + k1) * (i64)p.rs;
     };
     auto flush = [&](int slot, int k1) {
         double* sr = reinterpret_cast<double*>(smem);
@@ -98,10 +99,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     };
 
     // element n2 = tid + 256 q of a row: tile (tid / TILE) + (256 / TILE) q, offset tid % TILE
-    auto t_off = [&](int q) -> i64 {
-        const int n2 = tid + 256 * q;
-        return (i64)(n2 / DYNPY_T_TILE) * p.M1 * DYNPY_T_TILE + (n2 % DYNPY_T_TILE);
-    };
+    auto t_off = [&](int q) -> i64 { return tid + 256 * q; };
     int slot, k1;
     i64 item;
     const cd* src = row_ptr(u0, slot, k1, item);
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         for (int q = 0; q < 16; ++q) v[q] = nx[q];
         if constexpr (FIX) {
             const double mr = p.rsum[2 * item] * p.inv_n, mi = p.rsum[2 * item + 1] * p.inv_n;
-            const cd* rr = p.R + (i64)k1 * DYNPY_T_TILE;
+            const cd* rr = p.R + (i64)k1 * p.rs;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const cd r = ldg_cd(rr + t_off(q));
@@ -135,12 +133,11 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         int nslot = slot, nk1 = k1;
         i64 nitem = item;
         if (u + 1 < u1) src = row_ptr(u + 1, nslot, nk1, nitem);
-        if (u + 2 < u1 && tid < 4096 / DYNPY_T_TILE) {
+        if (p.pf_dist > 0 && u + p.pf_dist < u1 && tid == 0) {
             int s2, k2;
             i64 i2;
-            const cd* pf = row_ptr(u + 2, s2, k2, i2);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf + (i64)tid * p.M1 * DYNPY_T_TILE),
-                         "r"(DYNPY_T_TILE * 16) : "memory");
+            const cd* pf = row_ptr(u + p.pf_dist, s2, k2, i2);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(4096 * 16) : "memory");
         }
         // ---- step 2
 #pragma unroll
