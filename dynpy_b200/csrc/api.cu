@@ -420,8 +420,8 @@ static i64 dd_item_bytes(i64 N, i64 M) {
 int64_t dynpy_dd_workspace_bytes(int64_t n_frames, int64_t M, int64_t items) {
     if (items < 1) items = 1;
     int64_t need = items * dd_item_bytes(n_frames, M) + 1024;
-    int64_t stream = dd_stream_workspace_bytes(M, 1 << 22);  // ring + per-pair sums for up to 4M pairs
-    return need > stream ? need : stream;
+    int64_t fast = dd2_supported(M) ? dd2_workspace_bytes(M, items) : 0;
+    return need > fast ? need : fast;
 }
 
 int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
@@ -440,37 +440,9 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
     if (rc) return rc;
     const i64 N = n_frames;
     {
-        const char* sel = getenv("DYNPY_DD_PATH");  // "v1": previous generation kernels (A/B checks)
+        const char* sel = getenv("DYNPY_DD_PATH");  // "v1": generic word generator + engine (A/B checks)
         if (dd2_supported(M) && !(sel && sel[0] == 'v' && sel[1] == '1') && ws_bytes >= dd2_workspace_bytes(M, 1))
             return dd2_run(coords, N, pair_i, pair_j, n_pairs, a, b, c, spectrum, M, ws, ws_bytes, d->tw4096, d->n_sm, st);
-    }
-    if (dd_stream_supported(M, n_pairs) && ws_bytes >= dd_stream_workspace_bytes(M, n_pairs))
-        return dd_stream_run(coords, N, pair_i, pair_j, n_pairs, a, b, c, spectrum, M, ws, ws_bytes, d->tw4096, st);
-    if (dd_cols_supported(M)) {
-        // fused generator + column pass: workspace = rsum[2*cap] | T[cap*11][M]
-        const i64 per_item = (i64)DD_NSLOTS * M * (i64)sizeof(cd) + 16;
-        i64 capf = (ws_bytes - 1024) / per_item;
-        if (capf >= 1) {
-            const i64 items_all = (n_pairs + 1) / 2;
-            if (capf > items_all) capf = items_all;
-            double* rsum = (double*)ws;
-            cd* Tf = (cd*)((char*)ws + align_up(capf * 16, 256));
-            EpiParams epf;
-            memset(&epf, 0, sizeof(epf));
-            epf.out = spectrum;
-            epf.M = M;
-            epf.nslots = DD_NSLOTS;
-            const int acc_slot[DD_NSLOTS] = {0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6};
-            for (int s = 0; s < DD_NSLOTS; ++s) epf.acc_pack |= (unsigned long long)acc_slot[s] << (4 * s);
-            for (i64 it0 = 0; it0 < items_all; it0 += capf) {
-                const i64 cnt = items_all - it0 < capf ? items_all - it0 : capf;
-                DYNPY_CHECK(launch_cols_dd(coords, N, pair_i, pair_j, 2 * it0, n_pairs, cnt, a, b, c, Tf, M, rsum,
-                                           d->tw4096, d->n_sm, st), "dd fused columns");
-                DYNPY_CHECK(rows_acc_two_pass(epf, Tf, cnt * DD_NSLOTS, DD_NSLOTS, (int)(M / DYNPY_ROW_LEN), d->tw4096,
-                                              d->n_sm, st), "dd rows");
-            }
-            return DYNPY_OK;
-        }
     }
     i64 cap = (ws_bytes - 1024) / dd_item_bytes(N, M);
     if (cap < 1) {

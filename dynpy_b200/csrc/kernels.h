@@ -36,24 +36,11 @@ cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const 
 cudaError_t launch_simpson(const double* y, const double* x, i64 n, int n_cols, i64 col_stride, int mode,
                            double* out, cudaStream_t st);
 
-// persistent fused dipolar path (dd_stream.cu)
-bool dd_stream_supported(i64 M, i64 n_pairs);
-i64 dd_stream_workspace_bytes(i64 M, i64 n_pairs);
-int dd_stream_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c,
-                  double* S, i64 M, void* ws, i64 ws_bytes, const cd* tw, cudaStream_t st);
-
 // dipolar fast path (dd2.cu): warp-autonomous fused column kernel + row kernel v2
 bool dd2_supported(i64 M);
 i64 dd2_workspace_bytes(i64 M, i64 items);
 int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
             i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st);
-
-bool dd_cols_supported(i64 M);
-cudaError_t launch_cols_dd(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs, i64 items,
-                           double a, double b, double c, cd* T, i64 M, double* rsum, const cd* tw, int n_sm,
-                           cudaStream_t st);
-cudaError_t rows_acc_two_pass(const EpiParams& ep, cd* T, i64 n_fft, int nslots, int M1, const cd* tw, int n_sm,
-                              cudaStream_t st);
 
 // engine entry points (one translation unit per loader so they compile in parallel)
 cudaError_t forward_planar_acc(const PlanarLoader& ld, const EpiParams& ep, i64 n_fft, i64 M, int nslots, cd* T,
