@@ -420,7 +420,7 @@ static i64 dd_item_bytes(i64 N, i64 M) {
 int64_t dynpy_dd_workspace_bytes(int64_t n_frames, int64_t M, int64_t items) {
     if (items < 1) items = 1;
     int64_t need = items * dd_item_bytes(n_frames, M) + 1024;
-    int64_t fast = dd2_supported(M) ? dd2_workspace_bytes(M, items) : 0;
+    int64_t fast = dd2_supported(M) ? dd2_workspace_bytes(M, n_frames, items) : 0;
     return need > fast ? need : fast;
 }
 
@@ -441,7 +441,7 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
     const i64 N = n_frames;
     {
         const char* sel = getenv("DYNPY_DD_PATH");  // "v1": generic word generator + engine (A/B checks)
-        if (dd2_supported(M) && !(sel && sel[0] == 'v' && sel[1] == '1') && ws_bytes >= dd2_workspace_bytes(M, 1))
+        if (dd2_supported(M) && !(sel && sel[0] == 'v' && sel[1] == '1') && ws_bytes >= dd2_workspace_bytes(M, N, 1))
             return dd2_run(coords, N, pair_i, pair_j, n_pairs, a, b, c, spectrum, M, ws, ws_bytes, d->tw4096, d->n_sm, st);
     }
     i64 cap = (ws_bytes - 1024) / dd_item_bytes(N, M);

@@ -1,6 +1,7 @@
 // Host side of the dipolar fast path: fused generator + column kernel (dd_cols2.cuh) and the
 // accumulate-power row kernel (fft_rows2.cuh), batched through the T workspace.
 #include "dd_cols2.cuh"
+#include "dd_tpc.cuh"
 #include "fft_rows2.cuh"
 #include "kernels.h"
 #include <stdlib.h>
@@ -14,10 +15,11 @@ bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096
 // bytes of one padded transform of T
 static inline i64 t_bytes(i64 M) { return (M >> 12) * (i64)DYNPY_T_RS * (i64)sizeof(cd); }
 
-// workspace: R[M'] | TWT[M] | rsum[2*cap] | T[cap][11][M']   (M' = M1 * DYNPY_T_RS padded rows)
-i64 dd2_workspace_bytes(i64 M, i64 items) {
+// workspace: R[M'] | TWT[M] | rsum[2*cap] | Gs[2*cap][4][N] | T[cap][11][M']   (M' = M1 * DYNPY_T_RS padded rows)
+i64 dd2_workspace_bytes(i64 M, i64 N, i64 items) {
     if (items < 1) items = 1;
-    return t_bytes(M) + M * (i64)sizeof(cd) + align_up2(items * 16, 256) + items * DD_NSLOTS * t_bytes(M) + 512;
+    return t_bytes(M) + M * (i64)sizeof(cd) + align_up2(items * 16, 256) + align_up2(items * 64 * N, 256) +
+           items * DD_NSLOTS * t_bytes(M) + 1024;
 }
 
 template <int M1>
@@ -70,34 +72,76 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
     return cudaGetLastError();
 }
 
+template <int M1>
+static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
+    ProfScope prof(PROF_COLS, st);
+    const size_t smem = (size_t)(M1 / 2) * 128 * sizeof(cd);  // per-thread sample stash
+    cudaError_t e = cudaFuncSetAttribute(k_cols_tpc<M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_cols_tpc<M1><<<(M1 >= 64 ? 3 : 4) * n_sm, 128, smem, st>>>(p);
+    return cudaGetLastError();
+}
+static cudaError_t launch_cols_tpc(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
+    switch ((int)(p.M >> 12)) {
+        case 16: return launch_cols_tpc_M1<16>(p, n_sm, st);
+        case 32: return launch_cols_tpc_M1<32>(p, n_sm, st);
+        case 64: return launch_cols_tpc_M1<64>(p, n_sm, st);
+        case 50: return launch_cols_tpc_M1<50>(p, n_sm, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
             i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st) {
+    // column kernel: thread-per-column (dd_tpc.cuh) except for M1 = 64, whose 32-point in-register halves
+    // do not fit 168 registers without spilling (there the warp-exchange kernel of dd_cols2.cuh is faster);
+    // DYNPY_DD_COLS=warp|tpc overrides (A/B checks)
+    const char* sel = getenv("DYNPY_DD_COLS");
+    const bool tpc = sel ? sel[0] != 'w' : (M >> 12) != 64;
     const i64 items_all = (P + 1) / 2;
-    const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 512;
-    const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16;
-    i64 cap = (ws_bytes - fixed - 256) / per_item;
+    const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 1024;
+    const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16 + 64 * N;
+    i64 cap = (ws_bytes - fixed - 512) / per_item;
     if (cap < 1) {
-        set_error("dipolar fast path: workspace too small (need >= %lld bytes)", (long long)dd2_workspace_bytes(M, 1));
+        set_error("dipolar fast path: workspace too small (need >= %lld bytes)", (long long)dd2_workspace_bytes(M, N, 1));
         return DYNPY_ERR_WORKSPACE;
     }
     if (cap > items_all) cap = items_all;
     char* base = (char*)ws;
     cd* R = (cd*)base;
     cd* TWT = (cd*)(base + t_bytes(M));
-    double* rsum = (double*)(base + t_bytes(M) + M * (i64)sizeof(cd));
-    cd* T = (cd*)(base + t_bytes(M) + M * (i64)sizeof(cd) + align_up2(cap * 16, 256));
+    i64 off = t_bytes(M) + M * (i64)sizeof(cd);
+    double* rsum = (double*)(base + off);
+    off += align_up2(cap * 16, 256);
+    cd* Gs = (cd*)(base + off);
+    off += align_up2(cap * 64 * N, 256);
+    cd* T = (cd*)(base + off);
 
     ColsDD2Params cp;
     memset(&cp, 0, sizeof(cp));
     cp.X = X; cp.pi = pi; cp.pj = pj; cp.n_pairs = P; cp.N = N; cp.a = a; cp.b = b; cp.c = c;
     cp.M = M; cp.inv_M = 1.0 / (double)M; cp.twp = tw; cp.rsum = rsum;
-    k_fill_twt<<<4 * n_sm, 256, 0, st>>>(TWT, (int)(M >> 12), M, 1.0 / (double)M);
-    DYNPY_CHECK(cudaGetLastError(), "dd twiddle table");
-    cp.twt = TWT;
+    ColsTpcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.N = N; tp.M = M; tp.seeds = TWT;  // the seed table shares the twiddle-table region (never both in one call)
+    GeomParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.X = X; gp.pi = pi; gp.pj = pj; gp.n_pairs = P; gp.N = N; gp.a = a; gp.b = b; gp.c = c; gp.Gs = Gs; gp.rsum = rsum;
     // column transform of the all-ones series (for the mean removal of G_r)
-    cp.T = R; cp.items = 1; cp.ones = 1;
-    DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd ones columns");
-    cp.T = T; cp.ones = 0;
+    if (tpc) {
+        k_fill_seeds<<<16, 256, 0, st>>>(TWT, 1.0 / (double)M);
+        DYNPY_CHECK(cudaGetLastError(), "dd twiddle seeds");
+        tp.Gs = nullptr; tp.items = 1; tp.T = R;
+        DYNPY_CHECK(launch_cols_tpc(tp, n_sm, st), "dd ones columns");
+        tp.Gs = Gs; tp.T = T;
+    } else {
+        k_fill_twt<<<4 * n_sm, 256, 0, st>>>(TWT, (int)(M >> 12), M, 1.0 / (double)M);
+        DYNPY_CHECK(cudaGetLastError(), "dd twiddle table");
+        cp.twt = TWT;
+        cp.T = R; cp.items = 1; cp.ones = 1;
+        DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd ones columns");
+        cp.T = T; cp.ones = 0;
+    }
 
     Rows2Params rp;
     memset(&rp, 0, sizeof(rp));
@@ -109,9 +153,23 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     for (i64 it0 = 0; it0 < items_all; it0 += cap) {
         const i64 cnt = items_all - it0 < cap ? items_all - it0 : cap;
         DYNPY_CHECK(cudaMemsetAsync(rsum, 0, sizeof(double) * 2 * cnt, st), "dd rsum");
-        cp.pair0 = 2 * it0;
-        cp.items = cnt;
-        DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd columns");
+        if (tpc) {
+            gp.pair0 = 2 * it0;
+            gp.n_slots = 2 * cnt;
+            {
+                ProfScope prof(PROF_WORDS, st);
+                k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
+            }
+            DYNPY_CHECK(cudaGetLastError(), "dd geometry");
+            tp.items = cnt;
+            tp.pair0 = 2 * it0;
+            tp.n_pairs = P;
+            DYNPY_CHECK(launch_cols_tpc(tp, n_sm, st), "dd columns");
+        } else {
+            cp.pair0 = 2 * it0;
+            cp.items = cnt;
+            DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd columns");
+        }
         rp.items = cnt;
         const int plain[10] = {0, 1, 2, 3, 4, 6, 7, 8, 9, 10};
         const int gr[1] = {5};

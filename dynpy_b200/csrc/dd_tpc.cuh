@@ -1,0 +1,270 @@
+// dynpy_b200 — dipolar column pass, one THREAD per column (sm_100a).
+//
+// Two kernels per batch of pair-pairs ("items"):
+//
+//   k_dd_geom     distances.pdist_ortho (minimum image, distances.py:190-234) + the geometric part of
+//                 ddrax.cart_to_dipolar_from_df (ddrax.py:110-126): per pair-frame the unit vector
+//                 (x, y, z)/r and r^-3, written once as two double2 streams Gs[pair][2][N]: (x/r, y/r), (z/r, r^-3)
+//                 (32 B per pair-frame), plus the per-pair sum of r^-3 (for the mean of G_r).
+//                 Pure streaming: 48 B read, 32 B written per pair-frame.
+//
+//   k_cols_tpc    first pass of the zero-padded forward transform of all 11 series of an item.
+//                 M = M1 x 4096, sample n = 4096 n1 + n2.  A thread owns column n2 of one series:
+//                 it forms the series' H = M1/2 non-zero samples from the geometry streams
+//                 (Y2m in Cartesian closed form), and computes the M1-point column transform as a
+//                 radix-2 DIF split into two H-point transforms done entirely in registers by the
+//                 generated codelets (even k1: DFT_H(x), odd k1: DFT_H(x W_M1^n1); H = 25 or 32, 16, 8).
+//                 No shared memory, no barrier, no exchange between threads: consecutive threads are
+//                 consecutive columns, so every load and every 16-byte store of a warp is one
+//                 contiguous 256 / 512 byte run.  The inter-pass twiddles W_M^{n2 k1} run as one
+//                 complex-product chain per parity from two per-thread seeds.
+//
+// Per output point: (cost of the two codelets)/M1 + 8 (twiddle chain + product) + ~3 (series
+// formation) fp64 instructions = 26 (M1 = 50) / 24 (M1 = 64); 16 B stored, ~12 B loaded.
+#pragma once
+#include "codelets.cuh"
+#include "dd_device.cuh"
+#include "fft_engine.cuh"
+#include "fft_rows2.cuh"  // DYNPY_T_RS: row stride of T
+
+namespace dynpy {
+
+struct GeomParams {
+    const double* X;   // wrapped coordinates [atom][3][N]
+    const int* pi;
+    const int* pj;
+    i64 pair0;         // first pair of the batch
+    i64 n_pairs;       // total number of pairs
+    i64 n_slots;       // pair slots of the batch (2 * items; slots beyond n_pairs are zero-filled)
+    i64 N;
+    double a, b, c;
+    cd* Gs;            // [n_slots][2][N] double2 streams: (x/r, y/r) and (z/r, r^-3)
+    double* rsum;      // [n_slots] sums of r^-3 (zeroed by the caller)
+};
+
+// grid: (frame chunks of 1024, pair slots); 256 threads x 4 frames
+__global__ void __launch_bounds__(256) k_dd_geom(const GeomParams p) {
+    __shared__ double sred[8];
+    const i64 slot = blockIdx.y;
+    const i64 pr = p.pair0 + slot;
+    const bool exists = pr < p.n_pairs;
+    const double* xi = p.X;
+    const double* xj = p.X;
+    if (exists) {
+        xi += (i64)__ldg(p.pi + pr) * 3 * p.N;
+        xj += (i64)__ldg(p.pj + pr) * 3 * p.N;
+    }
+    cd* out = p.Gs + slot * 2 * p.N;
+    double rs = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const i64 f = (i64)blockIdx.x * 1024 + e * 256 + threadIdx.x;
+        if (f < p.N) {
+            double gx = 0.0, gy = 0.0, gz = 0.0, g3 = 0.0;
+            if (exists) {
+                double dx, dy, dz, sx, sy, sz;
+                axis_min(__ldg(xi + f), __ldg(xj + f), p.a, dx, sx);
+                axis_min(__ldg(xi + p.N + f), __ldg(xj + p.N + f), p.b, dy, sy);
+                axis_min(__ldg(xi + 2 * p.N + f), __ldg(xj + 2 * p.N + f), p.c, dz, sz);
+                const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+                double rinv = rsqrt(r2);
+                rinv = rinv * fma(-0.5 * r2, rinv * rinv, 1.5);  // one Newton step: r^-1 to ~1 ulp
+                gx = dx * rinv; gy = dy * rinv; gz = dz * rinv;
+                g3 = rinv * rinv * rinv;
+            }
+            out[f] = make_double2(gx, gy);
+            out[p.N + f] = make_double2(gz, g3);
+            rs += g3;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = rs;
+    __syncthreads();
+    if (threadIdx.x == 0 && exists) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sred[w];
+        atomicAdd(p.rsum + slot, t);
+    }
+}
+
+struct ColsTpcParams {
+    const cd* Gs;      // [2*items][2][N] geometry streams of the batch (nullptr: all-ones series, "ones" mode)
+    i64 items;
+    i64 pair0, n_pairs; // first pair of the batch / total pairs (pair q of the last item may not exist)
+    i64 N;
+    cd* T;             // [items][11][M1][DYNPY_T_RS]   (ones mode: [M1][DYNPY_T_RS])
+    i64 M;
+    const cd* seeds;   // [4096][2]: W_M^{n2}, W_M^{2 n2}
+};
+
+// twiddle seeds of every column (filled once per call)
+__global__ void k_fill_seeds(cd* seeds, double inv_M) {
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n2 < 4096) {
+        seeds[2 * n2] = w_exact(n2, inv_M);
+        seeds[2 * n2 + 1] = w_exact(2 * (i64)n2, inv_M);
+    }
+}
+
+// 16-byte streaming store: T is written once and read once by the row kernel, it must not push the
+// geometry streams (re-read by the 11 series of an item) out of L2
+__device__ __forceinline__ void st_stream(cd* p, cd v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+template <int H> struct ColCodelets;
+template <> struct ColCodelets<25> {
+    static __device__ __forceinline__ void even(cd (&v)[25]) { fft25(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[25]) { fft25_odd(v); }
+};
+template <> struct ColCodelets<32> {
+    static __device__ __forceinline__ void even(cd (&v)[32]) { fft32(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[32]) { fft32_odd(v); }
+};
+template <> struct ColCodelets<16> {
+    static __device__ __forceinline__ void even(cd (&v)[16]) { fft16(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[16]) { fft16_odd(v); }
+};
+template <> struct ColCodelets<8> {
+    static __device__ __forceinline__ void even(cd (&v)[8]) { fft8(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[8]) { fft8_odd(v); }
+};
+
+// Work units u = (item, column block of 128, slot), slot fastest, dealt round-robin to the CTAs: the 11
+// series of an (item, column block) run on 11 CTAs at about the same time and share the geometry
+// streams through L2.  Series formation has two branch-free families (keeps the kernel inside the
+// instruction cache):  complex  s (x + i y)^e  with s = c [r^-3] [z]  (Y21, Y22, F21, F22), and the
+// real series of the two pairs of an item packed as re + i im  (Y20, r^-3, F20).
+// 16-byte global -> shared copy that zero-fills when `on` is false
+__device__ __forceinline__ void cp_async16_zfill(cd* smem_dst, const cd* gsrc, bool on) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = on ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+
+template <int M1>
+__global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const ColsTpcParams p) {
+    constexpr int H = M1 / 2;
+    constexpr int NCB = 4096 / 128;
+    extern __shared__ double2 smem[];
+    // thread-private zone of H double2 at zone[j * 128]: landing area of the two geometry streams (one
+    // cp.async burst each: all H loads of a stream are in flight together, L2 latency is paid twice per
+    // series instead of once per frame), then the stash of the H samples for the odd half
+    cd* zone = smem + threadIdx.x;
+    const bool ones = p.Gs == nullptr;
+    const int nslots = ones ? 1 : 11;
+    const i64 units = (ones ? 1 : p.items) * NCB * nslots;
+    const int nfr = (int)(p.N < (i64)H * 4096 ? p.N : (i64)H * 4096);  // frames beyond M/2 do not exist
+    const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
+    const double KF = 1.5853309190424043;
+    constexpr i64 TS = (i64)M1 * DYNPY_T_RS;
+    const i64 N = p.N;
+
+    // stream A of a unit: (x/r, y/r) of the series' pair, or (z/r, r^-3) of pair p for the packed series
+    auto issue_stream = [&](i64 u, int which) {
+        if (u < units && !ones) {
+            const int slot = (int)(u % nslots);
+            const i64 ic = u / nslots;
+            const int n2 = (int)(ic % NCB) * 128 + threadIdx.x;
+            const i64 item = ic / NCB;
+            const bool packed = slot == 0 || slot == 5 || slot == 6;
+            const bool second = slot == 2 || slot == 4 || slot == 8 || slot == 10;
+            // packed: A = (z, r3) of p, B = (z, r3) of q;  complex: A = (x, y), B = (z, r3) of the series' pair
+            const i64 sl = packed ? (which ? 3 : 1) : (second ? 2 : 0) + which;
+            const cd* src = p.Gs + item * 4 * N + sl * N + n2;
+            const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+#pragma unroll
+            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * 128, src + (j << 12), j < jlim);  // (no read when off)
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue_stream(blockIdx.x, 0);
+    for (i64 u = blockIdx.x; u < units; u += gridDim.x) {
+        const int slot = (int)(u % nslots);
+        const i64 ic = u / nslots;
+        const int n2 = (int)(ic % NCB) * 128 + threadIdx.x;
+        const i64 item = ic / NCB;
+        const cd w1 = ldg_cd(p.seeds + 2 * n2), w2 = ldg_cd(p.seeds + 2 * n2 + 1);
+        cd* dst = p.T + (item * nslots + slot) * TS + n2;
+        // slot -> series (kernels.h): 0 Y20 p+iq | 1,2 Y21 p,q | 3,4 Y22 p,q | 5 r^-3 p+iq | 6 F20 p+iq | 7,8 F21 p,q | 9,10 F22 p,q
+        const bool packed = slot == 0 || slot == 5 || slot == 6;
+        const bool weighted = slot >= 6;                       // carries r^-3 (F2m)
+        const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;  // (x + i y)^1 z, else (x + i y)^2
+        const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
+        const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+        cd v[H];
+        if (ones) {
+#pragma unroll
+            for (int j = 0; j < H; ++j) v[j] = make_double2(j < jlim ? 1.0 : 0.0, 0.0);
+        } else {
+            // ---- stream A
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (packed) {
+                const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const cd zr = zone[j * 128];
+                    const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
+                    v[j].x = j < jlim ? (slot == 0 ? c : c * zr.y) * y : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const cd xy = zone[j * 128];
+                    v[j] = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                }
+            }
+            // ---- stream B into the same zone
+            issue_stream(u, 1);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (packed) {
+                const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const cd zr = zone[j * 128];
+                    const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
+                    v[j].y = (j < jlim && q_exists) ? (slot == 0 ? c : c * zr.y) * y : 0.0;
+                }
+            } else {
+                const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const cd zr = zone[j * 128];
+                    const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
+                    v[j] = make_double2(sc * v[j].x, sc * v[j].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) zone[j * 128] = v[j];
+        // even outputs
+        ColCodelets<H>::even(v);
+        {
+            cd w = w2;
+            st_stream(dst, v[0]);
+#pragma unroll
+            for (int a = 1; a < H; ++a) {
+                st_stream(dst + (i64)(2 * a) * DYNPY_T_RS, cmul(v[a], w));
+                if (a + 1 < H) w = cmul(w, w2);
+            }
+        }
+        // odd outputs
+#pragma unroll
+        for (int j = 0; j < H; ++j) v[j] = zone[j * 128];
+        issue_stream(u + gridDim.x, 0);  // the zone is free: next series' first stream lands under the odd half
+        ColCodelets<H>::odd(v);
+        {
+            cd w = w1;
+#pragma unroll
+            for (int a = 0; a < H; ++a) {
+                st_stream(dst + (i64)(2 * a + 1) * DYNPY_T_RS, cmul(v[a], w));
+                if (a + 1 < H) w = cmul(w, w2);
+            }
+        }
+    }
+}
+
+}  // namespace dynpy

@@ -38,7 +38,7 @@ cudaError_t launch_simpson(const double* y, const double* x, i64 n, int n_cols, 
 
 // dipolar fast path (dd2.cu): warp-autonomous fused column kernel + row kernel v2
 bool dd2_supported(i64 M);
-i64 dd2_workspace_bytes(i64 M, i64 items);
+i64 dd2_workspace_bytes(i64 M, i64 N, i64 items);
 int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
             i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st);
 

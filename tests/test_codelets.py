@@ -21,13 +21,15 @@ extern "C" int run_codelet(int id, double* io) {
         CASE(0, fft2, 2) CASE(1, fft4, 4) CASE(2, fft8, 8) CASE(3, fft16, 16)
         CASE(4, fft2_h1, 2) CASE(5, fft4_h2, 4) CASE(6, fft8_h4, 8) CASE(7, fft16_h8, 16)
         CASE(8, fft5, 5) CASE(9, fft25, 25) CASE(10, fft25_odd, 25)
+        CASE(11, fft32, 32) CASE(12, fft8_odd, 8) CASE(13, fft16_odd, 16) CASE(14, fft32_odd, 32)
     }
     return -1;
 }
 """
 # id, n, non-zero leading inputs, kind
 SPECS = [(0, 2, 2, ""), (1, 4, 4, ""), (2, 8, 8, ""), (3, 16, 16, ""), (4, 2, 1, ""), (5, 4, 2, ""), (6, 8, 4, ""),
-         (7, 16, 8, ""), (8, 5, 5, ""), (9, 25, 25, ""), (10, 25, 25, "odd50")]
+         (7, 16, 8, ""), (8, 5, 5, ""), (9, 25, 25, ""), (10, 25, 25, "odd"), (11, 32, 32, ""), (12, 8, 8, "odd"),
+         (13, 16, 16, "odd"), (14, 32, 32, "odd")]
 
 
 @pytest.fixture(scope="module")
@@ -56,7 +58,7 @@ def test_codelet_matches_numpy(lib, cid, n, nz, kind):
         io[2 * nz:] = np.nan  # structurally zero inputs must not be read
         assert lib.run_codelet(cid, io.ctypes.data) == n
         got = io[0::2] + 1j * io[1::2]
-        ref = np.fft.fft(np.concatenate([x, np.zeros(25)]))[1::2] if kind == "odd50" else np.fft.fft(x)
+        ref = np.fft.fft(np.concatenate([x, np.zeros(n)]))[1::2] if kind == "odd" else np.fft.fft(x)
         assert np.max(np.abs(got - ref)) <= 4e-16 * np.sqrt(n) * np.max(np.abs(ref))
 
 

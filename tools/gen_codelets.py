@@ -266,6 +266,10 @@ def main():
         ("fft4_h2", 4, 2, None, "zero-padded half"),
         ("fft8_h4", 8, 4, None, "zero-padded half"),
         ("fft16_h8", 16, 8, None, "zero-padded half"),
+        ("fft32", 32, None, None, ""),
+        ("fft8_odd", 8, None, [root(16, j) for j in range(8)], "odd outputs of a 16-point DFT of 8 leading non-zero inputs"),
+        ("fft16_odd", 16, None, [root(32, j) for j in range(16)], "odd outputs of a 32-point DFT of 16 leading non-zero inputs"),
+        ("fft32_odd", 32, None, [root(64, j) for j in range(32)], "odd outputs of a 64-point DFT of 32 leading non-zero inputs"),
         ("fft5", 5, None, None, ""),
         ("fft25", 25, None, None, "5 x 5"),
         ("fft25_odd", 25, None, [root(50, j) for j in range(25)],
