@@ -75,10 +75,12 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
 template <int M1>
 static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);
-    const size_t smem = (size_t)(M1 / 2) * 128 * sizeof(cd);  // per-thread sample stash
+    constexpr int TPC_THREADS = TpcShape<M1>::NT;
+    const size_t smem = (size_t)(M1 / 2) * TPC_THREADS * sizeof(cd);  // per-thread landing zone / sample stash
     cudaError_t e = cudaFuncSetAttribute(k_cols_tpc<M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_cols_tpc<M1><<<(M1 >= 64 ? 3 : 4) * n_sm, 128, smem, st>>>(p);
+    const int per_sm = TpcShape<M1>::PER_SM;
+    k_cols_tpc<M1><<<per_sm * n_sm, TPC_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 static cudaError_t launch_cols_tpc(const ColsTpcParams& p, int n_sm, cudaStream_t st) {

@@ -114,6 +114,14 @@ __device__ __forceinline__ void st_stream(cd* p, cd v) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// threads per CTA of the column kernel: 512 (one CTA per SM, 16 warps running the same straight-line code
+// close together, which is what keeps the instruction caches effective); 128 x 3 CTAs for M1 = 64, whose
+// 32-point halves need 168 registers
+template <int M1> struct TpcShape {
+    static constexpr int NT = M1 >= 64 ? 128 : 512;
+    static constexpr int PER_SM = M1 >= 64 ? 3 : 1;
+};
+
 template <int H> struct ColCodelets;
 template <> struct ColCodelets<25> {
     static __device__ __forceinline__ void even(cd (&v)[25]) { fft25(v); }
@@ -145,11 +153,12 @@ __device__ __forceinline__ void cp_async16_zfill(cd* smem_dst, const cd* gsrc, b
 }
 
 template <int M1>
-__global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const ColsTpcParams p) {
+__global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols_tpc(const ColsTpcParams p) {
     constexpr int H = M1 / 2;
-    constexpr int NCB = 4096 / 128;
+    constexpr int TPC_THREADS = TpcShape<M1>::NT;
+    constexpr int NCB = 4096 / TPC_THREADS;
     extern __shared__ double2 smem[];
-    // thread-private zone of H double2 at zone[j * 128]: landing area of the two geometry streams (one
+    // thread-private zone of H double2 at zone[j * TPC_THREADS]: landing area of the two geometry streams (one
     // cp.async burst each: all H loads of a stream are in flight together, L2 latency is paid twice per
     // series instead of once per frame), then the stash of the H samples for the odd half
     cd* zone = smem + threadIdx.x;
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
         if (u < units && !ones) {
             const int slot = (int)(u % nslots);
             const i64 ic = u / nslots;
-            const int n2 = (int)(ic % NCB) * 128 + threadIdx.x;
+            const int n2 = (int)(ic % NCB) * TPC_THREADS + threadIdx.x;
             const i64 item = ic / NCB;
             const bool packed = slot == 0 || slot == 5 || slot == 6;
             const bool second = slot == 2 || slot == 4 || slot == 8 || slot == 10;
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
             const cd* src = p.Gs + item * 4 * N + sl * N + n2;
             const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
 #pragma unroll
-            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * 128, src + (j << 12), j < jlim);  // (no read when off)
+            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * TPC_THREADS, src + (j << 12), j < jlim);  // (no read when off)
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
     for (i64 u = blockIdx.x; u < units; u += gridDim.x) {
         const int slot = (int)(u % nslots);
         const i64 ic = u / nslots;
-        const int n2 = (int)(ic % NCB) * 128 + threadIdx.x;
+        const int n2 = (int)(ic % NCB) * TPC_THREADS + threadIdx.x;
         const i64 item = ic / NCB;
         const cd w1 = ldg_cd(p.seeds + 2 * n2), w2 = ldg_cd(p.seeds + 2 * n2 + 1);
         cd* dst = p.T + (item * nslots + slot) * TS + n2;
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
         const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;  // (x + i y)^1 z, else (x + i y)^2
         const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
         const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+        __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)
         cd v[H];
         if (ones) {
 #pragma unroll
@@ -206,14 +216,14 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
                 const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * 128];
+                    const cd zr = zone[j * TPC_THREADS];
                     const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
                     v[j].x = j < jlim ? (slot == 0 ? c : c * zr.y) * y : 0.0;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
-                    const cd xy = zone[j * 128];
+                    const cd xy = zone[j * TPC_THREADS];
                     v[j] = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
                 }
             }
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
                 const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * 128];
+                    const cd zr = zone[j * TPC_THREADS];
                     const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
                     v[j].y = (j < jlim && q_exists) ? (slot == 0 ? c : c * zr.y) * y : 0.0;
                 }
@@ -232,14 +242,14 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
                 const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * 128];
+                    const cd zr = zone[j * TPC_THREADS];
                     const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
                     v[j] = make_double2(sc * v[j].x, sc * v[j].y);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < H; ++j) zone[j * 128] = v[j];
+        for (int j = 0; j < H; ++j) zone[j * TPC_THREADS] = v[j];
         // even outputs
         ColCodelets<H>::even(v);
         {
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(128, (M1 >= 64 ? 3 : 4)) k_cols_tpc(const Cols
         }
         // odd outputs
 #pragma unroll
-        for (int j = 0; j < H; ++j) v[j] = zone[j * 128];
+        for (int j = 0; j < H; ++j) v[j] = zone[j * TPC_THREADS];
         issue_stream(u + gridDim.x, 0);  // the zone is free: next series' first stream lands under the odd half
         ColCodelets<H>::odd(v);
         {
