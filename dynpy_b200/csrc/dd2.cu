@@ -125,6 +125,7 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     cp.M = M; cp.inv_M = 1.0 / (double)M; cp.twp = tw; cp.rsum = rsum;
     ColsTpcParams tp;
     memset(&tp, 0, sizeof(tp));
+    { const char* e = getenv("DYNPY_TPC_SYNC"); tp.sync_units = e ? atoi(e) : 1; }
     tp.N = N; tp.M = M; tp.seeds = TWT;  // the seed table shares the twiddle-table region (never both in one call)
     GeomParams gp;
     memset(&gp, 0, sizeof(gp));

@@ -97,6 +97,7 @@ struct ColsTpcParams {
     cd* T;             // [items][11][M1][DYNPY_T_RS]   (ones mode: [M1][DYNPY_T_RS])
     i64 M;
     const cd* seeds;   // [4096][2]: W_M^{n2}, W_M^{2 n2}
+    int sync_units;    // 1: CTA barrier once per series
 };
 
 // twiddle seeds of every column (filled once per call)
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;  // (x + i y)^1 z, else (x + i y)^2
         const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
         const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
-        __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)
+        if (p.sync_units) __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)
         cd v[H];
         if (ones) {
 #pragma unroll
