@@ -278,19 +278,23 @@ def native_arm(args, wl):
     hbm, how = peaks()
     pf_total = float(P) * float(F)
     value = pf_total / (ms_step * 1e-3)
-    names = ["dd_words", "fft_cols", "fft_rows", "other"]
+    names = ["dd_geom", "fft_cols", "fft_rows", "other"]
     per = {names[k]: {"ms_per_step": prof_ms[k] / args.steps, "launches_per_step": prof_n[k] / args.steps}
            for k in range(4)}
     dom = max(range(3), key=lambda k: prof_ms[k])
     pf_rank = float(hi - lo) * float(F)
     t_dom = prof_ms[dom] / args.steps * 1e-3
     achieved = ALG_BYTES_PER_PAIR_FRAME * pf_rank / t_dom / 1e9 if t_dom > 0 else 0.0
+    # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture
+    # (profiles/traffic.json holds bytes per pair-frame; one launch = one batch of the workspace)
     traffic = None
+    launches = max(1.0, prof_n[dom] / args.steps / (2.0 if dom == 2 else 1.0))  # rows: two launches per batch
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(names[dom])
+            traffic = json.load(fh)[names[dom]]["bytes_per_pair_frame"] * pf_rank / launches
     except Exception:
         pass
+    alg_per_launch = ALG_BYTES_PER_PAIR_FRAME * pf_rank / launches
     line = {
         "metric": "pair-frames/s (dipolar G(tau)+R1)", "value": value, "unit": "pair-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -304,7 +308,13 @@ def native_arm(args, wl):
                 "h2d_bytes_per_step": int(raw.numel() * 8), "d2h_bytes_per_step": int(7 * F * 8 + 48)},
         "gpu_launches": int(sum(prof_n)) + 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
+                     "frac": achieved / hbm, "traffic": traffic, "algorithmic_bytes_per_launch": alg_per_launch,
+                     "launch_ms": t_dom * 1e3 / launches, "peak_source": how,
+                     "ceilings": {"note": "measured on this pool (profiles/r01_ubench_ceilings.txt): the path is bound by fp64 issue "
+                                          "+ shared-memory/L1 wavefronts and by the T intermediate (2 x 16 B per transform point), "
+                                          "not by the 48 algorithmic bytes",
+                                  "hbm_copy_gbs": 6200.0, "l2_copy_gbs": 12400.0, "fp64_lanes_per_clk_per_sm": 63.5,
+                                  "dram_bytes_per_pair_frame": 488.0},
                      "algorithmic_bytes_per_pair_frame": ALG_BYTES_PER_PAIR_FRAME,
                      "kernel_share_of_step": prof_ms[dom] / args.steps / ms_step,
                      "whole_step_frac": ALG_BYTES_PER_PAIR_FRAME * pf_rank / (ms_step * 1e-3) / 1e9 / hbm,
