@@ -274,6 +274,7 @@ def native_arm(args, wl):
     ms_e2e, _ = timed(e2e_step, max(1, min(args.steps, 3)))
 
     if rank != 0:
+        dist.shutdown()
         return
     hbm, how = peaks()
     pf_total = float(P) * float(F)
@@ -323,7 +324,8 @@ def native_arm(args, wl):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(box, wl, F)
-    print(json.dumps(line))
+    dist.shutdown()
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -126,16 +126,16 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     ColsTpcParams tp;
     memset(&tp, 0, sizeof(tp));
     { const char* e = getenv("DYNPY_TPC_SYNC"); tp.sync_units = e ? atoi(e) : 1; }
-    tp.N = N; tp.M = M; tp.seeds = TWT;  // the seed table shares the twiddle-table region (never both in one call)
+    tp.N = N; tp.M = M; tp.rsum = rsum; tp.inv_n = 1.0 / (double)N; tp.seeds = TWT;  // the seed table shares the twiddle-table region (never both in one call)
     GeomParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.X = X; gp.pi = pi; gp.pj = pj; gp.n_pairs = P; gp.N = N; gp.a = a; gp.b = b; gp.c = c; gp.Gs = Gs; gp.rsum = rsum;
     // column transform of the all-ones series (for the mean removal of G_r)
     if (tpc) {
+        // the thread-per-column kernel removes the mean of r^-3 in the time domain (the sums are complete
+        // when it starts), so there is no all-ones transform and no mean-removing row launch
         k_fill_seeds<<<16, 256, 0, st>>>(TWT, 1.0 / (double)M);
         DYNPY_CHECK(cudaGetLastError(), "dd twiddle seeds");
-        tp.Gs = nullptr; tp.items = 1; tp.T = R;
-        DYNPY_CHECK(launch_cols_tpc(tp, n_sm, st), "dd ones columns");
         tp.Gs = Gs; tp.T = T;
     } else {
         k_fill_twt<<<4 * n_sm, 256, 0, st>>>(TWT, (int)(M >> 12), M, 1.0 / (double)M);
@@ -174,10 +174,15 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
             DYNPY_CHECK(launch_cols_dd2(cp, n_sm, st), "dd columns");
         }
         rp.items = cnt;
-        const int plain[10] = {0, 1, 2, 3, 4, 6, 7, 8, 9, 10};
-        const int gr[1] = {5};
-        DYNPY_CHECK(launch_rows2(rp, plain, 10, false, n_sm, st), "dd rows");
-        DYNPY_CHECK(launch_rows2(rp, gr, 1, true, n_sm, st), "dd rows (G_r)");
+        if (tpc) {
+            const int all[11] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+            DYNPY_CHECK(launch_rows2(rp, all, 11, false, n_sm, st), "dd rows");
+        } else {
+            const int plain[10] = {0, 1, 2, 3, 4, 6, 7, 8, 9, 10};
+            const int gr[1] = {5};
+            DYNPY_CHECK(launch_rows2(rp, plain, 10, false, n_sm, st), "dd rows");
+            DYNPY_CHECK(launch_rows2(rp, gr, 1, true, n_sm, st), "dd rows (G_r)");
+        }
     }
     return DYNPY_OK;
 }

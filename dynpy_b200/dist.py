@@ -20,6 +20,8 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout (CSV / JSON consumers)
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
@@ -28,6 +30,12 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
+
+
+def shutdown() -> None:
+    """Tear the process group down (no-op for single-process runs)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def rank_world() -> tuple[int, int]:
