@@ -58,10 +58,10 @@ static cudaError_t launch_cols_M1(const Loader& ld, cd* T, const cd* tw, i64 M, 
     return cudaGetLastError();
 }
 
-template <class Loader>
-static cudaError_t launch_cols50(const Loader& ld, cd* T, i64 M, i64 f0, i64 f1, int gy, cudaStream_t st) {
+template <int M1, class Loader>
+static cudaError_t launch_cols_tpcg(const Loader& ld, cd* T, i64 M, i64 f0, i64 f1, int gy, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);
-    k_cols50<Loader><<<dim3(DYNPY_ROW_LEN / 128, gy), 128, 0, st>>>(ld, T, M, 1.0 / (double)M, f0, f1, gy);
+    k_cols_tpcg<M1, Loader><<<dim3(DYNPY_ROW_LEN / 256, gy), 256, 0, st>>>(ld, T, 1.0 / (double)M, f0, f1, gy);
     return cudaGetLastError();
 }
 
@@ -69,12 +69,12 @@ template <class Loader>
 static cudaError_t launch_cols(int M1, const Loader& ld, cd* T, const cd* tw, i64 M, i64 f0, i64 f1, int gy,
                                cudaStream_t st) {
     switch (M1) {
-        case 50: return launch_cols50<Loader>(ld, T, M, f0, f1, gy, st);
+        case 50: return launch_cols_tpcg<50, Loader>(ld, T, M, f0, f1, gy, st);
         case 2: return launch_cols_M1<2, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 4: return launch_cols_M1<4, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 8: return launch_cols_M1<8, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
-        case 16: return launch_cols_M1<16, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
-        case 32: return launch_cols_M1<32, 128, Loader>(ld, T, tw, M, f0, f1, gy, st);
+        case 16: return launch_cols_tpcg<16, Loader>(ld, T, M, f0, f1, gy, st);
+        case 32: return launch_cols_tpcg<32, Loader>(ld, T, M, f0, f1, gy, st);
         case 64: return launch_cols_M1<64, 64, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 128: return launch_cols_M1<128, 32, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 256: return launch_cols_M1<256, 16, Loader>(ld, T, tw, M, f0, f1, gy, st);
@@ -113,7 +113,7 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
         i64 f0 = it0 * nslots, f1 = it1 * nslots < n_fft ? it1 * nslots : n_fft;
         i64 nb = f1 - f0;
         // first pass: (4096/C) tiles x gy CTAs
-        int tiles = M1 == 50 ? DYNPY_ROW_LEN / 128 : M1 <= 16 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / C
+        int tiles = (M1 == 50 || M1 == 32) ? DYNPY_ROW_LEN / 256 : M1 <= 16 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / C
         int gy1 = ceil_div_i(target, tiles);
         if (gy1 > nb) gy1 = (int)nb;
         if (gy1 < 1) gy1 = 1;

@@ -173,6 +173,7 @@ enum LoaderKind { LOAD_PLANAR = 0, LOAD_QR = 1, LOAD_SPECTRUM = 2 };
 // the sums over n of the re / im series of slot `bias_slot`; value - sum/N is transformed
 // (G_r = ACF of r^-3 - mean(r^-3), ddrax.py:292).
 struct PlanarLoader {
+    static constexpr bool DENSE = false;  // zero-padded series: samples n >= N are structurally zero
     const double* re;
     const double* im;
     i64 hi, lo, n_im_valid;
@@ -225,6 +226,7 @@ struct PlanarLoader {
 //   3: R2,-1(b)                    4: R2,-2(b)
 // |R2,+m|^2-spectra equal those of R2,-m (conjugate / sign), so +m columns reuse them.
 struct QrLoader {
+    static constexpr bool DENSE = false;
     const double* V;
     i64 N;       // frames
     i64 nnuc;    // nuclei in this shard
@@ -258,6 +260,7 @@ struct QrLoader {
 // Final transform: reads the accumulated spectrum S' (internal order) of accumulator f as a
 // purely real length-M series in natural frequency order.
 struct SpectrumLoader {
+    static constexpr bool DENSE = true;   // a full-length spectrum
     const double* S;
     i64 M;
     int M1;  // 1 for single-pass spectra
@@ -511,36 +514,59 @@ k_cols(Loader ld, cd* __restrict__ T, const cd* __restrict__ twp, i64 M, double 
     }
 }
 
-// ---------------------------------------------------------------- first pass, M1 = 50 (M = 204800)
-// Any loader, one thread per column n2: the 50-point column transform is a radix-2 DIF split into two
-// 25-point codelets (even k1: x[j] + x[j+25]; odd k1: (x[j] - x[j+25]) W_50^j), done one after the other
-// to stay inside the register file; the inter-pass twiddles W_M^{n2 k1} run as a chain per parity.
-// M = 204800 is the transform length for 65536 < N <= 102400 frames (22 % fewer points than 2^18).
-template <class Loader>
-__global__ void __launch_bounds__(128) k_cols50(Loader ld, cd* __restrict__ T, i64 M, double inv_M, i64 f_begin,
-                                                i64 f_end, int f_step) {
+// ---------------------------------------------------------------- first pass, one thread per column
+// Any loader, M1 in {16, 32, 50}: the M1-point column transform is a radix-2 DIF split into two
+// H = M1/2 point codelets done in registers (even k1: x[j] + x[j+H]; odd k1: (x[j] - x[j+H]) W_M1^j), one
+// after the other to stay inside the register file; the inter-pass twiddles W_M^{n2 k1} run as a chain
+// per parity.  Zero-padded loaders (series of N <= M/2 samples: Loader::DENSE == false) never touch
+// the upper half.  No shared memory, no barrier; consecutive threads are consecutive columns.
+// M = 204800 = 50 x 4096 is the transform length for 65536 < N <= 102400 frames.
+template <int H> struct HalfColumn;
+template <> struct HalfColumn<8> {
+    static __device__ __forceinline__ void even(cd (&v)[8]) { fft8(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[8]) { fft8_odd(v); }
+};
+template <> struct HalfColumn<16> {
+    static __device__ __forceinline__ void even(cd (&v)[16]) { fft16(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[16]) { fft16_odd(v); }
+};
+template <> struct HalfColumn<25> {
+    static __device__ __forceinline__ void even(cd (&v)[25]) { fft25(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[25]) { fft25_odd(v); }
+};
+
+template <int M1, class Loader>
+__global__ void __launch_bounds__(256, 2) k_cols_tpcg(Loader ld, cd* __restrict__ T, double inv_M, i64 f_begin,
+                                                      i64 f_end, int f_step) {
     constexpr int M2 = DYNPY_ROW_LEN;
+    constexpr int H = M1 / 2;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
     const cd w1 = w_exact(n2, inv_M);          // W_M^{n2}
     const cd w2 = w_exact(2 * (i64)n2, inv_M);  // W_M^{2 n2}
     for (i64 f = f_begin + blockIdx.y; f < f_end; f += f_step) {
         typename Loader::Ctx ctx = ld.begin(f);
-        cd* dst = T + ((f - f_begin) * 50) * (i64)M2 + n2;
+        cd* dst = T + ((f - f_begin) * M1) * (i64)M2 + n2;
 #pragma unroll 1
         for (int par = 0; par < 2; ++par) {
-            cd v[25];
+            cd v[H];
 #pragma unroll
-            for (int j = 0; j < 25; ++j) {
-                const cd a = ld.finish(ctx, ld.raw(ctx, (i64)j * M2 + n2));
-                const cd b = ld.finish(ctx, ld.raw(ctx, (i64)(j + 25) * M2 + n2));
-                v[j] = par ? csub(a, b) : cadd(a, b);
+            for (int j = 0; j < H; ++j) v[j] = ld.raw(ctx, (i64)j * M2 + n2);
+#pragma unroll
+            for (int j = 0; j < H; ++j) v[j] = ld.finish(ctx, v[j]);
+            if constexpr (Loader::DENSE) {
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const cd b = ld.finish(ctx, ld.raw(ctx, (i64)(j + H) * M2 + n2));
+                    v[j] = par ? csub(v[j], b) : cadd(v[j], b);
+                }
             }
-            if (par) fft25_odd(v); else fft25(v);
-            cd w = par ? w1 : make_double2(1.0, 0.0);
+            cd w;
+            if (par) { HalfColumn<H>::odd(v); w = w1; }
+            else { HalfColumn<H>::even(v); w = make_double2(1.0, 0.0); }
 #pragma unroll
-            for (int a = 0; a < 25; ++a) {
+            for (int a = 0; a < H; ++a) {
                 dst[(i64)(2 * a + par) * M2] = cmul(v[a], w);
-                w = cmul(w, w2);
+                if (a + 1 < H) w = cmul(w, w2);
             }
         }
     }
