@@ -187,8 +187,10 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
             const i64 sl = packed ? (which ? 3 : 1) : (second ? 2 : 0) + which;
             const cd* src = p.Gs + item * 4 * N + sl * N + n2;
             const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+            // rows j >= jlim are zero-filled (src-size 0: nothing is read; the address still lies inside the
+            // workspace, whose T region follows the geometry streams)
 #pragma unroll
-            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * TPC_THREADS, src + (j << 12), j < jlim);  // (no read when off)
+            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * TPC_THREADS, src + (j << 12), j < jlim);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };

@@ -60,8 +60,13 @@ static cudaError_t launch_cols_M1(const Loader& ld, cd* T, const cd* tw, i64 M, 
 
 template <int M1, class Loader>
 static cudaError_t launch_cols_tpcg(const Loader& ld, cd* T, i64 M, i64 f0, i64 f1, int gy, cudaStream_t st) {
+    const size_t smem = Loader::DENSE ? 0 : (size_t)(M1 / 2) * 256 * sizeof(cd);  // per-thread sample stash
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_cols_tpcg<M1, Loader>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     ProfScope prof(PROF_COLS, st);
-    k_cols_tpcg<M1, Loader><<<dim3(DYNPY_ROW_LEN / 256, gy), 256, 0, st>>>(ld, T, 1.0 / (double)M, f0, f1, gy);
+    k_cols_tpcg<M1, Loader><<<dim3(DYNPY_ROW_LEN / 256, gy), 256, smem, st>>>(ld, T, 1.0 / (double)M, f0, f1, gy);
     return cudaGetLastError();
 }
 

@@ -540,6 +540,8 @@ __global__ void __launch_bounds__(256, 2) k_cols_tpcg(Loader ld, cd* __restrict_
                                                       i64 f_end, int f_step) {
     constexpr int M2 = DYNPY_ROW_LEN;
     constexpr int H = M1 / 2;
+    extern __shared__ double2 smem[];
+    cd* stash = smem + threadIdx.x;  // zero-padded loaders: the H samples of this thread, kept for the odd half
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
     const cd w1 = w_exact(n2, inv_M);          // W_M^{n2}
     const cd w2 = w_exact(2 * (i64)n2, inv_M);  // W_M^{2 n2}
@@ -549,16 +551,24 @@ __global__ void __launch_bounds__(256, 2) k_cols_tpcg(Loader ld, cd* __restrict_
 #pragma unroll 1
         for (int par = 0; par < 2; ++par) {
             cd v[H];
+            if (Loader::DENSE || par == 0) {
 #pragma unroll
-            for (int j = 0; j < H; ++j) v[j] = ld.raw(ctx, (i64)j * M2 + n2);
+                for (int j = 0; j < H; ++j) v[j] = ld.raw(ctx, (i64)j * M2 + n2);
 #pragma unroll
-            for (int j = 0; j < H; ++j) v[j] = ld.finish(ctx, v[j]);
-            if constexpr (Loader::DENSE) {
+                for (int j = 0; j < H; ++j) v[j] = ld.finish(ctx, v[j]);
+                if constexpr (Loader::DENSE) {
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const cd b = ld.finish(ctx, ld.raw(ctx, (i64)(j + H) * M2 + n2));
-                    v[j] = par ? csub(v[j], b) : cadd(v[j], b);
+                    for (int j = 0; j < H; ++j) {
+                        const cd b = ld.finish(ctx, ld.raw(ctx, (i64)(j + H) * M2 + n2));
+                        v[j] = par ? csub(v[j], b) : cadd(v[j], b);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) stash[j * 256] = v[j];
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < H; ++j) v[j] = stash[j * 256];
             }
             cd w;
             if (par) { HalfColumn<H>::odd(v); w = w1; }
