@@ -82,7 +82,7 @@ static inline bool pow2(i64 m) { return m > 0 && (m & (m - 1)) == 0; }
 
 static int check_M(i64 M, i64 n) {
     if (!fft_length_ok(M)) {
-        set_error("transform length M=%lld must be a power of two in [32, 2^24] or 204800", (long long)M);
+        set_error("transform length M=%lld must be a power of two in [32, 2^24] or 4096 x {20, 24, 40, 50}", (long long)M);
         return DYNPY_ERR_INVALID;
     }
     if (n < 1 || 2 * n - 1 > M) {
@@ -134,13 +134,7 @@ int dynpy_profile_read(double* ms_host, int64_t* launches_host) {
     return DYNPY_OK;
 }
 
-int64_t dynpy_fft_length(int64_t n) {
-    int64_t m = 32;
-    while (m < 2 * n) m <<= 1;
-    // 50 x 4096 = 204800 >= 2n - 1 covers 65536 < n <= 102400 with 22 % fewer points than 2^18
-    if (m == ((int64_t)1 << 18) && 2 * n - 1 <= 50 * (int64_t)DYNPY_ROW_LEN) m = 50 * (int64_t)DYNPY_ROW_LEN;
-    return m;
-}
+int64_t dynpy_fft_length(int64_t n) { return fft_length_for(n); }
 
 int64_t dynpy_fft_workspace_bytes(int64_t M, int64_t n_fft) {
     if (M <= DYNPY_ROW_LEN) return 0;

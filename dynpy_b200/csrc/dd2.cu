@@ -10,7 +10,10 @@ namespace dynpy {
 
 static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
 
-bool dd2_supported(i64 M) { return M == 4096 * 16 || M == 4096 * 32 || M == 4096 * 64 || M == 4096 * 50; }
+bool dd2_supported(i64 M) {
+    const i64 m1 = M >> 12;
+    return (M & 4095) == 0 && (m1 == 16 || m1 == 20 || m1 == 24 || m1 == 32 || m1 == 40 || m1 == 50 || m1 == 64);
+}
 
 // bytes of one padded transform of T
 static inline i64 t_bytes(i64 M) { return (M >> 12) * (i64)DYNPY_T_RS * (i64)sizeof(cd); }
@@ -89,6 +92,9 @@ static cudaError_t launch_cols_tpc(const ColsTpcParams& p, int n_sm, cudaStream_
         case 32: return launch_cols_tpc_M1<32>(p, n_sm, st);
         case 64: return launch_cols_tpc_M1<64>(p, n_sm, st);
         case 50: return launch_cols_tpc_M1<50>(p, n_sm, st);
+        case 20: return launch_cols_tpc_M1<20>(p, n_sm, st);
+        case 24: return launch_cols_tpc_M1<24>(p, n_sm, st);
+        case 40: return launch_cols_tpc_M1<40>(p, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -99,7 +105,9 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     // do not fit 168 registers without spilling (there the warp-exchange kernel of dd_cols2.cuh is faster);
     // DYNPY_DD_COLS=warp|tpc overrides (A/B checks)
     const char* sel = getenv("DYNPY_DD_COLS");
-    const bool tpc = sel ? sel[0] != 'w' : (M >> 12) != 64;
+    const i64 m1 = M >> 12;
+    const bool warp_ok = m1 == 16 || m1 == 32 || m1 == 50 || m1 == 64;
+    const bool tpc = sel ? (sel[0] != 'w' || !warp_ok) : m1 != 64;
     const i64 items_all = (P + 1) / 2;
     const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 1024;
     const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16 + 64 * N;

@@ -130,6 +130,18 @@ template <> struct ColCodelets<25> {
     static __device__ __forceinline__ void even(cd (&v)[25]) { fft25(v); }
     static __device__ __forceinline__ void odd(cd (&v)[25]) { fft25_odd(v); }
 };
+template <> struct ColCodelets<10> {
+    static __device__ __forceinline__ void even(cd (&v)[10]) { fft10(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[10]) { fft10_odd(v); }
+};
+template <> struct ColCodelets<12> {
+    static __device__ __forceinline__ void even(cd (&v)[12]) { fft12(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[12]) { fft12_odd(v); }
+};
+template <> struct ColCodelets<20> {
+    static __device__ __forceinline__ void even(cd (&v)[20]) { fft20(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[20]) { fft20_odd(v); }
+};
 template <> struct ColCodelets<32> {
     static __device__ __forceinline__ void even(cd (&v)[32]) { fft32(v); }
     static __device__ __forceinline__ void odd(cd (&v)[32]) { fft32_odd(v); }

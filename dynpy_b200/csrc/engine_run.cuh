@@ -75,6 +75,9 @@ static cudaError_t launch_cols(int M1, const Loader& ld, cd* T, const cd* tw, i6
                                cudaStream_t st) {
     switch (M1) {
         case 50: return launch_cols_tpcg<50, Loader>(ld, T, M, f0, f1, gy, st);
+        case 20: return launch_cols_tpcg<20, Loader>(ld, T, M, f0, f1, gy, st);
+        case 24: return launch_cols_tpcg<24, Loader>(ld, T, M, f0, f1, gy, st);
+        case 40: return launch_cols_tpcg<40, Loader>(ld, T, M, f0, f1, gy, st);
         case 2: return launch_cols_M1<2, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 4: return launch_cols_M1<4, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
         case 8: return launch_cols_M1<8, 256, Loader>(ld, T, tw, M, f0, f1, gy, st);
@@ -118,7 +121,7 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
         i64 f0 = it0 * nslots, f1 = it1 * nslots < n_fft ? it1 * nslots : n_fft;
         i64 nb = f1 - f0;
         // first pass: (4096/C) tiles x gy CTAs
-        int tiles = (M1 == 50 || M1 == 32) ? DYNPY_ROW_LEN / 256 : M1 <= 16 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / C
+        int tiles = M1 <= 50 ? DYNPY_ROW_LEN / 256 : M1;  // == 4096 / (columns per CTA)
         int gy1 = ceil_div_i(target, tiles);
         if (gy1 > nb) gy1 = (int)nb;
         if (gy1 < 1) gy1 = 1;

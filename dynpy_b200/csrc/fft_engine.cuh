@@ -33,9 +33,22 @@ typedef long long i64;
 
 #define DYNPY_ROW_LEN 4096  // M2 of the two-pass split
 
-// transform lengths the engine implements: powers of two in [32, 2^24] and 50 * 4096
+// transform lengths the engine implements: powers of two in [32, 2^24] and M1 * 4096 for the mixed-radix
+// column plans M1 = 20, 24, 40, 50 (thread-per-column kernels with 10-, 12-, 20- and 25-point codelets)
 static inline bool fft_length_ok(long long M) {
-    return (M >= 32 && M <= (1ll << 24) && (M & (M - 1)) == 0) || M == 50ll * DYNPY_ROW_LEN;
+    if (M >= 32 && M <= (1ll << 24) && (M & (M - 1)) == 0) return true;
+    return M == 20ll * DYNPY_ROW_LEN || M == 24ll * DYNPY_ROW_LEN || M == 40ll * DYNPY_ROW_LEN || M == 50ll * DYNPY_ROW_LEN;
+}
+// smallest implemented length >= 2n - 1 (any such M gives the reference's linear ACF, qrax.py:153)
+static inline long long fft_length_for(long long n) {
+    long long m = 32;
+    while (m < 2 * n) m <<= 1;
+    const int mixed[4] = {20, 24, 40, 50};
+    for (int k = 0; k < 4; ++k) {
+        const long long c = (long long)mixed[k] * DYNPY_ROW_LEN;
+        if (c >= 2 * n - 1 && c < m) m = c;
+    }
+    return m;
 }
 #ifndef DYNPY_ROWS_MINB
 #define DYNPY_ROWS_MINB 2   // resident CTAs per SM the row kernel is compiled for
@@ -515,7 +528,7 @@ k_cols(Loader ld, cd* __restrict__ T, const cd* __restrict__ twp, i64 M, double 
 }
 
 // ---------------------------------------------------------------- first pass, one thread per column
-// Any loader, M1 in {16, 32, 50}: the M1-point column transform is a radix-2 DIF split into two
+// Any loader, M1 in {16, 20, 24, 32, 40, 50}: the M1-point column transform is a radix-2 DIF split into two
 // H = M1/2 point codelets done in registers (even k1: x[j] + x[j+H]; odd k1: (x[j] - x[j+H]) W_M1^j), one
 // after the other to stay inside the register file; the inter-pass twiddles W_M^{n2 k1} run as a chain
 // per parity.  Zero-padded loaders (series of N <= M/2 samples: Loader::DENSE == false) never touch
@@ -529,6 +542,18 @@ template <> struct HalfColumn<8> {
 template <> struct HalfColumn<16> {
     static __device__ __forceinline__ void even(cd (&v)[16]) { fft16(v); }
     static __device__ __forceinline__ void odd(cd (&v)[16]) { fft16_odd(v); }
+};
+template <> struct HalfColumn<10> {
+    static __device__ __forceinline__ void even(cd (&v)[10]) { fft10(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[10]) { fft10_odd(v); }
+};
+template <> struct HalfColumn<12> {
+    static __device__ __forceinline__ void even(cd (&v)[12]) { fft12(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[12]) { fft12_odd(v); }
+};
+template <> struct HalfColumn<20> {
+    static __device__ __forceinline__ void even(cd (&v)[20]) { fft20(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[20]) { fft20_odd(v); }
 };
 template <> struct HalfColumn<25> {
     static __device__ __forceinline__ void even(cd (&v)[25]) { fft25(v); }

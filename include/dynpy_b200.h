@@ -55,10 +55,10 @@ int dynpy_device_sm_count(void);
 int dynpy_profile_enable(int on);
 int dynpy_profile_read(double* ms_host, int64_t* launches_host);
 
-/* Padded transform length used for a series of n samples: max(32, 2^ceil(log2(2n))), except
- * 204800 = 50 x 4096 for 65536 < n <= 102400 (22 % fewer points than 2^18; radix-5 column pass).
- * Any M >= 2n-1 gives the same linear ACF as the reference's n=2N (qrax.py:153).  Every entry point
- * accepts M = a power of two in [32, 2^24] or 204800. */
+/* Padded transform length used for a series of n samples: the smallest of 2^k (k >= 5) and
+ * 4096 x {20, 24, 40, 50} that is >= 2n-1 (e.g. 204800 for 81920 < n <= 102400: 22 % fewer points than
+ * 2^18; mixed-radix column pass).  Any M >= 2n-1 gives the same linear ACF as the reference's n=2N
+ * (qrax.py:153).  Every entry point accepts M = a power of two in [32, 2^24] or 4096 x {20, 24, 40, 50}. */
 int64_t dynpy_fft_length(int64_t n);
 
 /* Bytes of workspace that let `n_fft` transforms of length M be in flight in the two-pass

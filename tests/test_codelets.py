@@ -22,6 +22,7 @@ extern "C" int run_codelet(int id, double* io) {
         CASE(4, fft2_h1, 2) CASE(5, fft4_h2, 4) CASE(6, fft8_h4, 8) CASE(7, fft16_h8, 16)
         CASE(8, fft5, 5) CASE(9, fft25, 25) CASE(10, fft25_odd, 25)
         CASE(11, fft32, 32) CASE(12, fft8_odd, 8) CASE(13, fft16_odd, 16) CASE(14, fft32_odd, 32)
+        CASE(15, fft10, 10) CASE(16, fft10_odd, 10) CASE(17, fft12, 12) CASE(18, fft12_odd, 12) CASE(19, fft20, 20) CASE(20, fft20_odd, 20)
     }
     return -1;
 }
@@ -29,7 +30,8 @@ extern "C" int run_codelet(int id, double* io) {
 # id, n, non-zero leading inputs, kind
 SPECS = [(0, 2, 2, ""), (1, 4, 4, ""), (2, 8, 8, ""), (3, 16, 16, ""), (4, 2, 1, ""), (5, 4, 2, ""), (6, 8, 4, ""),
          (7, 16, 8, ""), (8, 5, 5, ""), (9, 25, 25, ""), (10, 25, 25, "odd"), (11, 32, 32, ""), (12, 8, 8, "odd"),
-         (13, 16, 16, "odd"), (14, 32, 32, "odd")]
+         (13, 16, 16, "odd"), (14, 32, 32, "odd"), (15, 10, 10, ""), (16, 10, 10, "odd"), (17, 12, 12, ""),
+         (18, 12, 12, "odd"), (19, 20, 20, ""), (20, 20, 20, "odd")]
 
 
 @pytest.fixture(scope="module")

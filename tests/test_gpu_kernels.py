@@ -24,6 +24,17 @@ def ops():
     return o
 
 
+def expected_fft_length(n):
+    """dynpy_fft_length: smallest of 2^k and 4096 x {20, 24, 40, 50} that is >= 2n - 1 (and >= 32)."""
+    m = 32
+    while m < 2 * n:
+        m <<= 1
+    for m1 in (20, 24, 40, 50):
+        if m1 * 4096 >= 2 * n - 1 and m1 * 4096 < m:
+            m = m1 * 4096
+    return m
+
+
 def dev(x, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).cuda()
 
@@ -34,7 +45,7 @@ def nerr(got, ref):
 
 # ------------------------------------------------------------------ engine: all plans
 @pytest.mark.parametrize("N", [1, 5, 16, 17, 33, 100, 316, 700, 1025, 2048,       # single pass M = 32 .. 4096
-                               2049, 5000, 9000, 20000, 40000, 70000, 100000,   # M1 = 2 .. 64
+                               2049, 5000, 9000, 20000, 36000, 45000, 60000, 70000, 100000, 120000,  # M1 = 2 .. 64 (20, 24, 40, 50 mixed radix)
                                150000, 300000, 600000])                          # M1 = 128 .. 512
 def test_wk_sum_complex_all_plans(ops, N):
     rng = np.random.default_rng(N)
@@ -43,13 +54,13 @@ def test_wk_sum_complex_all_plans(ops, N):
     z *= np.exp(-np.arange(N) / (0.3 * N + 1))[None]
     spec = ops.wk_acf_sum(dev(z.real), dev(z.imag))
     M = spec.numel()
-    assert M == (204800 if 65536 < N <= 102400 else max(32, 1 << int(np.ceil(np.log2(2 * N)))))
+    assert M == expected_fft_length(N)
     acf = ops.ifft_acf(spec, N, 1.0 / (M * N)).cpu().numpy()[0]
     ref = sum(orc.wiener_khinchin(z[s]) for s in range(S))
     assert nerr(acf, ref) < 1e-12, nerr(acf, ref)
 
 
-@pytest.mark.parametrize("N", [65537, 80000, 102400])
+@pytest.mark.parametrize("N", [82000, 90000, 102400])
 def test_wk_mixed_radix_length_matches_power_of_two(ops, N):
     """M = 50 x 4096 (radix-5 column pass) and M = 2^18 give the same linear ACF (any M >= 2N-1 does)."""
     rng = np.random.default_rng(N)
@@ -191,8 +202,11 @@ def test_simpson(ops, n, mode):
 @pytest.mark.parametrize("F,P,budget_mb", [
     (5000, 7, 64),        # M = 16384  (M1 = 4: generic engine, not the fast path)
     (20000, 9, 64),       # M = 65536  (M1 = 16), odd pair count
-    (40000, 6, 4096),     # M = 131072 (M1 = 32)
-    (70000, 5, 200),      # M = 204800 (M1 = 50, mixed radix), odd pair count, several batches
+    (36000, 5, 4096),     # M = 81920  (M1 = 20, mixed radix 2 x 10)
+    (45000, 4, 4096),     # M = 98304  (M1 = 24, mixed radix 2 x 12)
+    (60000, 6, 4096),     # M = 131072 (M1 = 32)
+    (70000, 5, 200),      # M = 163840 (M1 = 40, mixed radix 2 x 20), odd pair count, several batches
+    (90000, 5, 200),      # M = 204800 (M1 = 50, mixed radix 2 x 25), odd pair count, several batches
     (102400, 4, 4096),    # M = 204800 at its largest N (all 25 x 4096 frames in use)
     (110000, 3, 4096),    # M = 262144 (M1 = 64)
 ])

@@ -38,6 +38,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.dynpy_fft_length(100000) == 204800  # 50 x 4096 covers 65536 < n <= 102400
     assert lib.dynpy_fft_length(65536) == 131072
     assert lib.dynpy_fft_length(102401) == 262144
+    assert lib.dynpy_fft_length(36000) == 20 * 4096 and lib.dynpy_fft_length(45000) == 24 * 4096
+    assert lib.dynpy_fft_length(70000) == 40 * 4096 and lib.dynpy_fft_length(32768) == 65536
     assert lib.dynpy_fft_length(1) == 32
     assert lib.dynpy_fft_workspace_bytes(4096, 10) == 0
     assert lib.dynpy_fft_workspace_bytes(8192, 3) == 3 * 8192 * 16

@@ -270,6 +270,12 @@ def main():
         ("fft8_odd", 8, None, [root(16, j) for j in range(8)], "odd outputs of a 16-point DFT of 8 leading non-zero inputs"),
         ("fft16_odd", 16, None, [root(32, j) for j in range(16)], "odd outputs of a 32-point DFT of 16 leading non-zero inputs"),
         ("fft32_odd", 32, None, [root(64, j) for j in range(32)], "odd outputs of a 64-point DFT of 32 leading non-zero inputs"),
+        ("fft10", 10, None, None, "2 x 5"),
+        ("fft10_odd", 10, None, [root(20, j) for j in range(10)], "odd outputs of a 20-point DFT of 10 leading non-zero inputs"),
+        ("fft12", 12, None, None, "4 x 3"),
+        ("fft12_odd", 12, None, [root(24, j) for j in range(12)], "odd outputs of a 24-point DFT of 12 leading non-zero inputs"),
+        ("fft20", 20, None, None, "4 x 5"),
+        ("fft20_odd", 20, None, [root(40, j) for j in range(20)], "odd outputs of a 40-point DFT of 20 leading non-zero inputs"),
         ("fft5", 5, None, None, ""),
         ("fft25", 25, None, None, "5 x 5"),
         ("fft25_odd", 25, None, [root(50, j) for j in range(25)],
