@@ -53,8 +53,32 @@ def _select_frames(start_prod, end_prod, sample_freq):
     return sel
 
 
-def _read_blocks(path, nat, header_lines, cols, printed):
-    """Return (symbols, xyz[F, A, 3] in file units) for the 1-indexed printed frames."""
+def _read_blocks(path, nat, header_lines, cols, printed, scale_div=1.0, pin=False):
+    """(symbols, xyz[F, A, 3] / scale_div) for the 1-indexed printed frames, parsed by the native
+    multi-threaded reader of the C-ABI library (csrc/ingest.cpp: mmap, parallel newline index,
+    std::from_chars).  `pin` puts the array in page-locked memory for the H2D copy."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    printed = np.ascontiguousarray(np.asarray(printed, dtype=np.int64))
+    F = len(printed)
+    if pin and torch.cuda.is_available():
+        host = torch.empty((F, nat, 3), dtype=torch.float64, pin_memory=True)
+    else:
+        host = torch.empty((F, nat, 3), dtype=torch.float64)
+    sym = C.create_string_buffer(8 * nat)
+    rc = lib.dynpy_parse_md_blocks_host(os.fsencode(path), nat, header_lines, cols[0], printed.ctypes.data, F,
+                                        float(scale_div), host.data_ptr(), C.cast(sym, C.c_void_p), 0)
+    _lib.check(rc, "dynpy_parse_md_blocks_host")
+    raw = sym.raw
+    symbols = [normsym(raw[8 * a:8 * a + 8].split(b"\0", 1)[0].decode()) for a in range(nat)]
+    return symbols, host
+
+
+def _read_blocks_py(path, nat, header_lines, cols, printed):
+    """Pure-Python restatement of the same block reader (test checker for the native one):
+    (symbols, xyz[F, A, 3] in file units) for the 1-indexed printed frames."""
     blk = nat + header_lines
     with open(path, "r") as fh:
         lines = fh.read().split("\n")
@@ -98,11 +122,11 @@ def PARSE_MD(PD, traj, device=None):
     printed = _select_frames(PD.start_prod, PD.end_prod, PD.sample_freq)
     if fmt == "xyz":
         name = _find(traj_dir, ".xyz", ".xyz")
-        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (0, 1, 2, 3), printed)
+        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (0, 1, 2, 3), printed, 0.529177, pin=True)
     elif fmt == "Tinker":
         name = _find(traj_dir, "arc", ".arc")
         print("reading " + name)
-        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (1, 2, 3, 4), printed)
+        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (1, 2, 3, 4), printed, 0.529177, pin=True)
     elif fmt == "QE":
         if 'symbols' not in PD.__dict__.keys():
             print("Error: Missing required input variable symbols in class ParseDynamics for parsing QE.")
@@ -113,12 +137,13 @@ def PARSE_MD(PD, traj, device=None):
         print("MD_format not provided or not recognized. Implemented formats are 'QE', 'Tinker', and 'xyz'. "
               "Do you need to parse MD trajectories?")
         sys.exit(2)
-    pos = torch.from_numpy(np.ascontiguousarray((xyz / 0.529177).transpose(1, 2, 0))).to(device)
+    # [F][A][3] (pinned host) -> device -> the kernels' [A][3][F] layout (transpose on the device)
+    pos = xyz.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
     frames = printed.astype(np.int64) * int(PD.md_print_freq)
     vel = None
     if PD.parse_vel:
         vname = _find(traj_dir, ".vel", ".vel")
         cols = (0, 1, 2, 3) if fmt == "xyz" else (1, 2, 3, 4)
-        _, v = _read_blocks(os.path.join(traj_dir, vname), PD.nat, 2, cols, printed)
-        vel = torch.from_numpy(np.ascontiguousarray((v / 0.529177).transpose(1, 2, 0))).to(device)
+        _, v = _read_blocks(os.path.join(traj_dir, vname), PD.nat, 2, cols, printed, 0.529177, pin=True)
+        vel = v.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
     return Trajectory(pos=pos, symbols=sym, frames=frames, vel=vel)

@@ -176,6 +176,20 @@ int dynpy_sr_angmom_f64(const double* pos, const double* vel, int64_t n_atoms, i
 int dynpy_simpson_f64(const double* y, const double* x, int64_t n, int n_cols, int64_t col_stride,
                       int mode, double* out, dynpy_stream_t stream);
 
+/* ---- trajectory ingestion (HOST function; no GPU needed) -----------------------------------------
+ * replaces the text handling of parseMD.parse_xyz / parse_tinker_md (parseMD.py:177-278):
+ * blocks of  <header_lines> lines + nat atom lines  "[cols...] sym x y z [cols...]";
+ *   first_col     column of the symbol (0: xyz, 1: Tinker .arc); x y z follow it
+ *   printed_host  1-indexed printed frame numbers to keep, ascending  [n_printed]
+ *   scale_div     every value is DIVIDED by it (0.529177: Angstrom -> bohr exactly like the reference)
+ *   out_host      [n_printed][nat][3] fp64 (caller-owned, may be pinned memory)
+ *   symbols_host  optional [nat][8] NUL-padded raw symbol tokens of the first kept frame
+ *   n_threads     <= 0: all hardware threads
+ * Fortran 'D' exponents are accepted; conversion is correctly rounded (== Python float()). */
+int dynpy_parse_md_blocks_host(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
+                               const int64_t* printed_host, int64_t n_printed, double scale_div,
+                               double* out_host, char* symbols_host, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

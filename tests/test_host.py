@@ -129,6 +129,40 @@ def test_parse_tinker_arc(tmp_path):
     np.testing.assert_allclose(tr.pos.numpy()[:, :, 0], np.round(traj[:, :, 1], 8) / 0.529177, rtol=0, atol=1e-12)
 
 
+def test_native_block_reader_matches_python_reader(tmp_path):
+    """csrc/ingest.cpp against the pure-Python restatement: bit-identical doubles for plain, signed,
+    exponent, Fortran-D and tab/CRLF formatted numbers, frame sub-sampling, no trailing newline."""
+    from dynpy_b200 import _lib, parseMD
+    rng = np.random.default_rng(5)
+    nat, nfr = 7, 23
+    path = tmp_path / "t.arc"
+    fmts = ["%14.8f", "%+.10e", "%.17g", "%12.6f"]
+    with open(path, "w", newline="") as fh:
+        for f in range(nfr):
+            fh.write("%d title %d\n box line\n" % (nat, f))
+            for a in range(nat):
+                v = rng.normal(size=3) * 10.0 ** rng.integers(-3, 4)
+                toks = [(fmts[(f + a + d) % 4] % v[d]) for d in range(3)]
+                if (f + a) % 5 == 0:
+                    toks = [t.replace("e", "D") for t in toks]
+                sep = "\t" if a % 3 == 0 else "  "
+                eol = "\r\n" if f % 4 == 0 else "\n"
+                last = (f == nfr - 1 and a == nat - 1)
+                fh.write(("%5d%sX%d%s" % (a + 1, sep, a, sep)) + sep.join(toks) + "  7 8 9" + ("" if last else eol))
+    printed = np.array([2, 3, 7, 11, 23])
+    sym_n, got = parseMD._read_blocks(str(path), nat, 2, (1, 2, 3, 4), printed, 0.529177)
+    sym_p, ref = parseMD._read_blocks_py(str(path), nat, 2, (1, 2, 3, 4), printed)
+    assert sym_n == sym_p
+    np.testing.assert_array_equal(got.numpy(), ref / 0.529177)
+    # errors are loud: file too short, malformed number
+    with pytest.raises(_lib.DynpyError, match="fewer than"):
+        parseMD._read_blocks(str(path), nat, 2, (1, 2, 3, 4), np.array([24]))
+    bad = tmp_path / "bad.xyz"
+    bad.write_text("1\nc\nH 0.0 abc 1.0\n")
+    with pytest.raises(_lib.DynpyError, match="cannot parse 'abc'"):
+        parseMD._read_blocks(str(bad), 1, 2, (0, 1, 2, 3), np.array([1]))
+
+
 # ------------------------------------------------------------------ topology / pair indexing
 def test_topology_numbering_and_pair_selection_match_oracle():
     from dynpy_b200 import DDparse, synth, topology
