@@ -289,7 +289,7 @@ def native_arm(args, wl):
     # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture
     # (profiles/traffic.json holds bytes per pair-frame; one launch = one batch of the workspace)
     traffic = None
-    launches = max(1.0, prof_n[dom] / args.steps / (2.0 if dom == 2 else 1.0))  # rows: two launches per batch
+    launches = max(1.0, prof_n[dom] / args.steps)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             traffic = json.load(fh)[names[dom]]["bytes_per_pair_frame"] * pf_rank / launches
