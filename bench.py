@@ -189,6 +189,11 @@ def native_arm(args, wl):
     import torch.distributed as tdist
 
     from dynpy_b200 import _lib, ddrax, dist, ops, synth
+    # stdout carries exactly one JSON line: anything a library prints while the job runs (NCCL's version
+    # banner, for one) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -325,6 +330,8 @@ def native_arm(args, wl):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(box, wl, F)
     dist.shutdown()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
