@@ -38,10 +38,8 @@ static cudaError_t launch_cols_dd2_M1(const ColsDD2Params& p, int n_sm, cudaStre
 
 static cudaError_t launch_cols_dd2(const ColsDD2Params& p, int n_sm, cudaStream_t st) {
     switch ((int)(p.M >> 12)) {
-        case 16: return launch_cols_dd2_M1<16>(p, n_sm, st);
-        case 32: return launch_cols_dd2_M1<32>(p, n_sm, st);
+        case 32: return launch_cols_dd2_M1<32>(p, n_sm, st);  // A/B checks only (DYNPY_DD_COLS=warp)
         case 64: return launch_cols_dd2_M1<64>(p, n_sm, st);
-        case 50: return launch_cols_dd2_M1<50>(p, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -106,7 +104,7 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     // DYNPY_DD_COLS=warp|tpc overrides (A/B checks)
     const char* sel = getenv("DYNPY_DD_COLS");
     const i64 m1 = M >> 12;
-    const bool warp_ok = m1 == 16 || m1 == 32 || m1 == 50 || m1 == 64;
+    const bool warp_ok = m1 == 32 || m1 == 64;
     const bool tpc = sel ? (sel[0] != 'w' || !warp_ok) : m1 != 64;
     const i64 items_all = (P + 1) / 2;
     const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 1024;

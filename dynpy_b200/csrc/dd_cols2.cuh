@@ -5,7 +5,8 @@
 // the zero-padded forward FFT of wiener_khinchin (ddrax.py:276-285) for all 11 real series of a
 // pair: nothing but the four-step intermediate T is written.
 //
-// Decomposition M = M1 x 4096, M1 = 8 R1 in {16, 32, 64} or M1 = 50; sample n = 4096 n1 + n2.
+// Decomposition M = M1 x 4096, M1 = 8 R1 (used for M1 = 64; M1 <= 50 goes through the thread-per-column
+// kernel of dd_tpc.cuh); sample n = 4096 n1 + n2.
 //   * a WARP owns CW = 32/R1 adjacent columns n2 (R1 threads per column, 8 points per thread);
 //     the only data exchange of the M1-point column transform is inside the warp (4.5 KB of
 //     shared memory per warp, __syncwarp), there is no CTA-wide barrier in the kernel;
@@ -18,10 +19,6 @@
 //   * the work list (item, 16-column tile) is cut into equal contiguous ranges per CTA, item-major, so
 //     the whole grid writes into the T blocks of the same few items at any time (TLB reach); the
 //     inter-pass twiddles of a tile are 8 table look-ups per thread (table filled once per call).
-// M1 = 50 (M = 204800, the length used for 65536 < N <= 102400 frames): 5 threads per column, 6 columns
-// per warp (30 lanes), 5 frames per thread; radix-2 DIF split into the even (x) and odd (x W_50^n1)
-// 25-point transforms, each 5 x 5: fft5 over q (n1 = 5 q + m), twiddle W_25^{m a1}, exchange, fft5
-// over m; outputs k1 = 2 (a1 + 5 a2) + parity, 10 per thread.
 // The mean of r^-3 (G_r is the ACF of r^-3 - <r^-3>, ddrax.py:292) is NOT subtracted here: the
 // per-pair sums go to rsum[] and the row kernel subtracts mean x (column transform of the
 // all-ones series), which is linear and exact; `ones` mode produces that table.
@@ -63,18 +60,17 @@ __device__ __forceinline__ void cp_async8_(double* smem_dst, const double* gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");  // 8-byte copies exist only as .ca
 }
 
-// compile-time shape of the column kernel for a given M1
+// compile-time shape of the column kernel for a given M1 = 8 R1
 template <int M1> struct ColShape {
-    static constexpr bool MR = (M1 == 50);          // mixed radix 2 x 5 x 5
-    static constexpr int TPC = MR ? 5 : M1 / 8;     // threads per column
-    static constexpr int CW = MR ? 6 : 32 / TPC;    // columns per warp
-    static constexpr int NFR = MR ? 5 : 4;          // frames (non-zero samples) per thread
-    static constexpr int NTW = MR ? 10 : 8;         // outputs == inter-pass twiddles per thread
+    static constexpr int TPC = M1 / 8;              // threads per column == first radix R1
+    static constexpr int CW = 32 / TPC;             // columns per warp
+    static constexpr int NFR = 4;                   // frames (non-zero samples) per thread
+    static constexpr int NTW = 8;                   // outputs == inter-pass twiddles per thread
     static constexpr int NWARP = 4;                 // warps per CTA; the CTA owns NWARP*CW adjacent columns
     static constexpr int TCOLS = CW * NWARP;
-    static constexpr int NTILE = (4096 + TCOLS - 1) / TCOLS;
-    static constexpr int WSLOTS = MR ? 2 * 25 * CW : (M1 + M1 / 8) * CW;  // exchange buffer of one warp (cd units)
-    static constexpr int NTW1 = MR ? 50 : 64;       // step-1 twiddle table entries
+    static constexpr int NTILE = 4096 / TCOLS;
+    static constexpr int WSLOTS = (M1 + M1 / 8) * CW;  // exchange buffer of one warp (cd units)
+    static constexpr int NTW1 = 64;                 // step-1 twiddle table entries
     static constexpr size_t smem_bytes() {
         return (size_t)NWARP * WSLOTS * sizeof(cd) + (size_t)NFR * 6 * 128 * sizeof(double) + (size_t)NTW * 128 * sizeof(cd) +
                2 * DD2_MAX_IDX * sizeof(int) + NTW1 * sizeof(cd);
@@ -84,16 +80,15 @@ template <int M1> struct ColShape {
 template <int M1>
 __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     typedef ColShape<M1> SH;
-    constexpr bool MR = SH::MR;
     constexpr int R1 = SH::TPC, CW = SH::CW, NFR = SH::NFR, NTW = SH::NTW, NWARP = SH::NWARP, NTILE = SH::NTILE;
     constexpr int WSLOTS = SH::WSLOTS;
-    constexpr int QH = MR ? 5 : R1 / 2;  // non-zero inputs of a step-1 butterfly
-    constexpr int NIT = MR ? 1 : 8 / R1; // step-1 butterflies per thread
+    constexpr int QH = R1 / 2;  // non-zero inputs of a step-1 butterfly
+    constexpr int NIT = 8 / R1; // step-1 butterflies per thread
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     const int c = lane % CW;
-    const int bb = lane / CW;            // MR: lanes 30, 31 get bb == 5 and stay idle
+    const int bb = lane / CW;
     const bool lane_on = bb < R1;
     cd* sm = smem + wid * WSLOTS;
     // thread-private staging of the NEXT pair's coordinates: value v of this thread at stage[v*128] ...
@@ -102,20 +97,9 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     cd* stw = smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + threadIdx.x;
     // ... the atom indices of the pairs this CTA will visit (filled once) ...
     int* sidx = reinterpret_cast<int*>(smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + NTW * 128);
-    // ... and the step-1 twiddles: W_M1^{m k} as [k][m] (pow2), or W_25^{m a1} as [a1][m] then W_50^{5q+m} as [q][m]
+    // ... and the step-1 twiddles W_M1^{m k} as [k][m]
     cd* stw1 = smem + NWARP * WSLOTS + (NFR * 6 * 128) / 2 + NTW * 128 + (2 * DD2_MAX_IDX * (int)sizeof(int)) / (int)sizeof(cd);
-    if constexpr (MR) {
-        if (threadIdx.x < 25) {
-            const int a = threadIdx.x / 5, m = threadIdx.x % 5;
-            double sn, cs;
-            sincospi(2.0 * (double)((m * a) % 25) / 25.0, &sn, &cs);
-            stw1[threadIdx.x] = make_double2(cs, -sn);
-            sincospi(2.0 * (double)(5 * a + m) / 50.0, &sn, &cs);
-            stw1[25 + threadIdx.x] = make_double2(cs, -sn);
-        }
-    } else {
-        if (threadIdx.x < 64) stw1[threadIdx.x] = ldg_cd(p.twp + (4096 / M1) * (threadIdx.x & 7) * (threadIdx.x >> 3));
-    }
+    if (threadIdx.x < 64) stw1[threadIdx.x] = ldg_cd(p.twp + (4096 / M1) * (threadIdx.x & 7) * (threadIdx.x >> 3));
     auto slot_of = [&](int row) { return (row + (row >> 3)) * CW + c; };
 
     const int items = p.ones ? 1 : (int)p.items;
@@ -132,39 +116,12 @@ __global__ void __launch_bounds__(128, 3) k_cols_dd2(const ColsDD2Params p) {
     bool on = false;  // this thread owns a real column (lane in use and n2 < 4096)
     cd tw[NTW];
     // n1 of this thread's fs-th frame, and k1 of its j-th output
-    auto n1_of = [&](int fs) -> int { return MR ? 5 * fs + bb : (fs % QH) * 8 + bb + (fs / QH) * R1; };
-    auto k1_of = [&](int j) -> int { return MR ? 2 * (bb + 5 * (j % 5)) + j / 5 : bb + R1 * j; };
+    auto n1_of = [&](int fs) -> int { return (fs % QH) * 8 + bb + (fs / QH) * R1; };
+    auto k1_of = [&](int j) -> int { return bb + R1 * j; };
     auto col_of = [&](int tile) -> int { return (tile * NWARP + wid) * CW + c; };
     // one series of the current (item, slot): NFR samples per thread -> column transform -> T
     auto emit = [&](const cd (&smp)[NFR], cd* dst) {
-        if constexpr (MR) {
-#pragma unroll
-            for (int par = 0; par < 2; ++par) {
-                cd u[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) u[q] = par ? cmul(smp[q], stw1[25 + 5 * q + (lane_on ? bb : 0)]) : smp[q];
-                fft5(u);
-                if (lane_on) {
-                    sm[(par * 25 + bb) * CW + c] = u[0];
-#pragma unroll
-                    for (int a = 1; a < 5; ++a) sm[(par * 25 + a * 5 + bb) * CW + c] = cmul(u[a], stw1[5 * a + bb]);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int par = 0; par < 2; ++par) {
-                cd v[5];
-#pragma unroll
-                for (int m = 0; m < 5; ++m) v[m] = lane_on ? sm[(par * 25 + bb * 5 + m) * CW + c] : make_double2(0.0, 0.0);
-                fft5(v);
-                if (on) {
-#pragma unroll
-                    for (int a2 = 0; a2 < 5; ++a2)
-                        dst[(2 * (bb + 5 * a2) + par) * DYNPY_T_RS] = cmul(v[a2], tw[par * 5 + a2]);
-                }
-            }
-            __syncwarp();
-        } else {
+        {
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int m = bb + it * R1;
