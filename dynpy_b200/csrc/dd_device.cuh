@@ -7,8 +7,26 @@ namespace dynpy {
 
 // np.mod(x, L) (universe.py:301-304 via distances.modv): C fmod, then the sign fix-up numpy
 // applies (npy_divmod): a non-zero remainder with the wrong sign gets +L (may round to L).
-__device__ __forceinline__ double np_mod(double x, double L) {
-    double m = fmod(x, L);
+// The C fmod itself is computed without the library's iterative routine when the quotient is small:
+// q = trunc(x / L) is off by at most one, r = fma(-q, L, x) is EXACT for the right q (the remainder of
+// fmod is always representable), and a wrong q shows as |r| >= |L| or a sign opposite to x.
+__device__ __forceinline__ double fmod_exact(double x, double L, double inv_L) {
+    const double t = x * inv_L;  // approximate quotient (inv_L = 1/L): q below may be off by one either way
+    if (!(fabs(t) < 1.0e12)) return fmod(x, L);  // huge quotients, inf, nan: library routine
+    double q = trunc(t);
+    double r = fma(-q, L, x);
+    const double aL = fabs(L);
+    if (fabs(r) >= aL) {  // |q| one too small
+        q += (t < 0.0) ? -1.0 : 1.0;
+        r = fma(-q, L, x);
+    } else if (r != 0.0 && ((r < 0.0) != (x < 0.0))) {  // |q| one too large
+        q -= (t < 0.0) ? -1.0 : 1.0;
+        r = fma(-q, L, x);
+    }
+    return r == 0.0 ? copysign(0.0, x) : r;
+}
+__device__ __forceinline__ double np_mod(double x, double L, double inv_L) {
+    double m = fmod_exact(x, L, inv_L);
     if (m != 0.0) {
         if ((L < 0.0) != (m < 0.0)) m = __dadd_rn(m, L);
     } else {
@@ -16,6 +34,7 @@ __device__ __forceinline__ double np_mod(double x, double L) {
     }
     return m;
 }
+__device__ __forceinline__ double np_mod(double x, double L) { return np_mod(x, L, 1.0 / L); }
 // ------------------------------------------------------------------ minimum image
 // Literal restatement of the candidate loop of pdist_ortho (distances.py:203-233): 27 images
 // in (aa,bb,cc) order, pxi = xi + aa*a, d = pxi - xj, r2 = dx*dx + dy*dy + dz*dz left to

@@ -392,8 +392,10 @@ __device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3]
             double t = b[k]; b[k] = b[i]; b[i] = t;
         }
 #pragma unroll
+        const double ipiv = 1.0 / A[k][k];
+#pragma unroll
         for (int i = k + 1; i < 3; ++i) {
-            const double l = A[i][k] / A[k][k];
+            const double l = A[i][k] * ipiv;
 #pragma unroll
             for (int j = 0; j < 3; ++j) if (j >= k) A[i][j] -= l * A[k][j];
             b[i] -= l * b[k];
@@ -417,50 +419,73 @@ __device__ __forceinline__ void cross3(const double a[3], const double b[3], dou
     o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
 __device__ __forceinline__ void normalize3(double v[3]) {
-    const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    v[0] /= n; v[1] /= n; v[2] /= n;
+    // v / |v| through rsqrt + two Newton steps (error ~1 ulp, like sqrt + 3 divisions at a fifth of the instructions)
+    const double s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double r = rsqrt(s);
+    r = r * fma(-0.5 * s, r * r, 1.5);
+    r = r * fma(-0.5 * s, r * r, 1.5);
+    v[0] *= r; v[1] *= r; v[2] *= r;
 }
 
 // thread = (frame, molecule); SR_func1 (SRrax.py:438-510):
 //   r, v relative to the mass-weighted mean; R = sum(r^2 1 - r r^T) unweighted; I mass-weighted;
 //   L' = sum r x v unweighted; omega = solve(R, L'); body axes from two minimum-image pair
 //   vectors; omega_b = ax^-1 omega; I_b = ax^-1 I ax; J = I_b omega_b.
+// NAT > 0: atoms per molecule known at compile time (positions and velocities stay in registers between
+// the centre-of-mass pass and the tensor pass); NAT == 0: run-time count, two passes over memory.
+template <int NAT>
 __global__ void __launch_bounds__(128)
 k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 N, const int* __restrict__ mol_atoms,
-            i64 n_mol, int nat, const double* __restrict__ mass, const int* __restrict__ axis_atoms, int axis_rule,
+            i64 n_mol, int nat_rt, const double* __restrict__ mass, const int* __restrict__ axis_atoms, int axis_rule,
             double ca, double cb, double cc, double inv_dt, i64 n_out, double* __restrict__ J,
             double* __restrict__ omega, double* __restrict__ axes) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 m = blockIdx.y;
     if (t >= n_out) return;
     const i64 fr = vel ? t : t + 1;  // frame whose positions are used
+    const int nat = NAT > 0 ? NAT : nat_rt;
     const int* at = mol_atoms + m * nat;
-    double msum = 0.0, cp[3] = {0, 0, 0}, cv[3] = {0, 0, 0};
-    for (int k = 0; k < nat; ++k) {
-        const double* p = pos + (i64)at[k] * 3 * N;
-        const double mk = mass[k];
-        msum += mk;
+    constexpr int NR = NAT > 0 ? NAT : 1;
+    double rx[NR][3], vx[NR][3], mk_[NR];
+    auto fetch = [&](int k, double (&x)[3], double (&v)[3]) {
+        const double* p = pos + (i64)__ldg(at + k) * 3 * N + fr;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            const double x = p[d * N + fr];
-            const double v = vel ? vel[((i64)at[k] * 3 + d) * N + fr] : (x - p[d * N + fr - 1]) * inv_dt;
-            cp[d] += mk * x; cv[d] += mk * v;
+            x[d] = p[d * N];
+            v[d] = vel ? vel[((i64)__ldg(at + k) * 3 + d) * N + fr] : (x[d] - p[d * N - 1]) * inv_dt;
+        }
+    };
+    double msum = 0.0, cp[3] = {0, 0, 0}, cv[3] = {0, 0, 0};
+    if constexpr (NAT > 0) {
+#pragma unroll
+        for (int k = 0; k < NAT; ++k) {
+            fetch(k, rx[k], vx[k]);
+            mk_[k] = __ldg(mass + k);
+        }
+#pragma unroll
+        for (int k = 0; k < NAT; ++k) {
+            msum += mk_[k];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { cp[d] += mk_[k] * rx[k][d]; cv[d] += mk_[k] * vx[k][d]; }
+        }
+    } else {
+        for (int k = 0; k < nat; ++k) {
+            double x[3], v[3];
+            fetch(k, x, v);
+            const double mk = mass[k];
+            msum += mk;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { cp[d] += mk * x[d]; cv[d] += mk * v[d]; }
         }
     }
     const double im = 1.0 / msum;
 #pragma unroll
     for (int d = 0; d < 3; ++d) { cp[d] *= im; cv[d] *= im; }
     double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rv[3] = {0, 0, 0};
-    for (int k = 0; k < nat; ++k) {
-        const double* p = pos + (i64)at[k] * 3 * N;
-        const double mk = mass[k];
+    auto tensor_terms = [&](const double (&x)[3], const double (&vv)[3], double mk) {
         double r[3], v[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const double x = p[d * N + fr];
-            const double vv = vel ? vel[((i64)at[k] * 3 + d) * N + fr] : (x - p[d * N + fr - 1]) * inv_dt;
-            r[d] = x - cp[d]; v[d] = vv - cv[d];
-        }
+        for (int d = 0; d < 3; ++d) { r[d] = x[d] - cp[d]; v[d] = vv[d] - cv[d]; }
         const double xx = r[0] * r[0], yy = r[1] * r[1], zz = r[2] * r[2];
         R[0][0] += yy + zz; R[1][1] += xx + zz; R[2][2] += xx + yy;
         R[0][1] += -r[0] * r[1]; R[0][2] += -r[0] * r[2]; R[1][2] += -r[1] * r[2];
@@ -469,22 +494,36 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
         double c3[3];
         cross3(r, v, c3);
         rv[0] += c3[0]; rv[1] += c3[1]; rv[2] += c3[2];
+    };
+    if constexpr (NAT > 0) {
+#pragma unroll
+        for (int k = 0; k < NAT; ++k) tensor_terms(rx[k], vx[k], mk_[k]);
+    } else {
+        for (int k = 0; k < nat; ++k) {
+            double x[3], v[3];
+            fetch(k, x, v);
+            tensor_terms(x, v, mass[k]);
+        }
     }
     R[1][0] = R[0][1]; R[2][0] = R[0][2]; R[2][1] = R[1][2];
     I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
     double o[3];
     solve3(R, rv, o);
-    // body axes from the two pair vectors (wrapped coordinates, 27-image minimum image)
+    // body axes from the two pair vectors (wrapped coordinates)
     const int* ax4 = axis_atoms + m * 4;
+    const double ica = 1.0 / ca, icb = 1.0 / cb, icc = 1.0 / cc;
     double dvec[2][3];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const double* pa = pos + (i64)ax4[2 * h] * 3 * N;
         const double* pb = pos + (i64)ax4[2 * h + 1] * 3 * N;
-        MinImage mi = min_image27(np_mod(pa[fr], ca), np_mod(pa[N + fr], cb), np_mod(pa[2 * N + fr], cc),
-                                  np_mod(pb[fr], ca), np_mod(pb[N + fr], cb), np_mod(pb[2 * N + fr], cc), ca, cb, cc,
-                                  1.0e300);
-        dvec[h][0] = mi.dx; dvec[h][1] = mi.dy; dvec[h][2] = mi.dz;
+        // per-axis minimum image: the same (x_i + s a) - x_j candidates as the 27-image loop of pdist_ortho and
+        // the same winner unless two of the 27 sums tie exactly (bonded atoms are far from half a box apart);
+        // 9 candidate evaluations instead of 81 — this kernel is instruction-bound, not HBM-bound, otherwise
+        double s2;
+        axis_min(np_mod(pa[fr], ca, ica), np_mod(pb[fr], ca, ica), ca, dvec[h][0], s2);
+        axis_min(np_mod(pa[N + fr], cb, icb), np_mod(pb[N + fr], cb, icb), cb, dvec[h][1], s2);
+        axis_min(np_mod(pa[2 * N + fr], cc, icc), np_mod(pb[2 * N + fr], cc, icc), cc, dvec[h][2], s2);
     }
     double X[3], Y[3], Z[3];
     if (axis_rule == 1) {
@@ -534,10 +573,19 @@ cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const 
     for (i64 m0 = 0; m0 < n_mol; m0 += 65535) {
         i64 cnt = n_mol - m0 < 65535 ? n_mol - m0 : 65535;
         dim3 grid((unsigned)((n_out + 127) / 128), (unsigned)cnt);
-        k_sr_angmom<<<grid, 128, 0, st>>>(pos, vel, N, mol_atoms + m0 * nat, cnt, nat, mass, axis_atoms + m0 * 4,
-                                          axis_rule, a, b, c, inv_dt, n_out, J ? J + m0 * 3 * n_out : nullptr,
-                                          omega ? omega + m0 * 3 * n_out : nullptr,
-                                          axes ? axes + m0 * 9 * n_out : nullptr);
+#define SR_LAUNCH(NATC)                                                                                             \
+    k_sr_angmom<NATC><<<grid, 128, 0, st>>>(pos, vel, N, mol_atoms + m0 * nat, cnt, nat, mass, axis_atoms + m0 * 4,   \
+                                            axis_rule, a, b, c, inv_dt, n_out, J ? J + m0 * 3 * n_out : nullptr,       \
+                                            omega ? omega + m0 * 3 * n_out : nullptr,                                   \
+                                            axes ? axes + m0 * 9 * n_out : nullptr)
+        switch (nat) {  // water, methyl / ammonia-like, methane, acetonitrile; anything else: run-time loop
+            case 3: SR_LAUNCH(3); break;
+            case 4: SR_LAUNCH(4); break;
+            case 5: SR_LAUNCH(5); break;
+            case 6: SR_LAUNCH(6); break;
+            default: SR_LAUNCH(0); break;
+        }
+#undef SR_LAUNCH
     }
     return cudaGetLastError();
 }

@@ -145,7 +145,10 @@ def test_qr_spectrum(ops, S, N):
 def test_wrap_bit_exact(ops):
     rng = np.random.default_rng(3)
     L = 30.651558
-    x = np.concatenate([rng.uniform(-3 * L, 3 * L, 5000), [0.0, -0.0, L, -L, -1e-18, 1e-18, 2 * L, -1e-300, 5e-324]])
+    k = np.arange(-60, 61) * L  # near-integer quotients: the fast exact-fmod path must fix q by one
+    x = np.concatenate([rng.uniform(-3 * L, 3 * L, 5000), [0.0, -0.0, L, -L, -1e-18, 1e-18, 2 * L, -1e-300, 5e-324],
+                        k, np.nextafter(k, np.inf), np.nextafter(k, -np.inf), rng.uniform(-1e7 * L, 1e7 * L, 2000),
+                        rng.uniform(-1e11 * L, 1e11 * L, 500), rng.uniform(-1e15 * L, 1e15 * L, 500), [1e300, -1e300]])
     got = ops.wrap(dev(x), L).cpu().numpy()
     np.testing.assert_array_equal(got, np.mod(x, L))
     assert got.max() <= L

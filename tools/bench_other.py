@@ -43,6 +43,8 @@ def sr():
     for c in range(3):
         ops.wk_acf_sum(J[:, c, :].contiguous(), pack_real_pairs=True, M=M, spectrum=spec[c])
     return ops.ifft_acf(spec, F - 1, 1.0 / (float(M) * (F - 1) * nmol))
+ms_k, _ = timed(lambda: ops.sr_angmom(pos, mol_atoms, mass, axis_atoms, 0, (L, L, L), 1000.0, want_omega=False, want_axes=False))
+print("SR  k_sr_angmom alone: %.2f ms (%.0f GB/s of the 120 B per molecule-frame)" % (ms_k, nmol * (F - 1) * 120 / ms_k * 1e3 / 1e9))
 ms, acf = timed(sr)
 print("SR  %d CH4 x %d frames: %.1f ms  %.3e molecule-frames/s  (120 B each -> %.0f GB/s algorithmic)  cols/rows %s" %
       (nmol, F - 1, ms, nmol * (F - 1) / ms * 1e3, nmol * (F - 1) * 120 / ms * 1e3 / 1e9, prof(sr)))
