@@ -38,6 +38,11 @@ WORKLOADS = {
                  name="cfg5: dipolar, 512 H2O x 1e6 frames, intermolecular H-H pairs, gapless rmax"),
     "small": dict(nmol=32, frames=20_000, pair_type="all", seed=2,
                   name="small: dipolar, 32 H2O x 2e4 frames, all H-H pairs, gapless rmax"),
+    # the other two mechanisms (not the headline metric; same JSON contract, their own units)
+    "cfg3": dict(kind="sr", nmol=512, frames=100_000, seed=3,
+                 name="cfg3: spin-rotation, 512 CH4 x 1e5 frames (angular momenta + 3 ACFs per molecule + rate)"),
+    "cfg4": dict(kind="qr", nuclei=8192, frames=65_536, seed=4,
+                 name="cfg4 shape: quadrupolar, 8192 nuclei per GPU x 65536 frames x 6 EFG components (5 ACFs + rates)"),
 }
 
 
@@ -335,6 +340,125 @@ def native_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ other mechanisms
+def other_arm(args, wl):
+    """Quadrupolar (cfg4 shape) and spin-rotation (cfg3) hot paths: same measurement contract as the dipolar arm
+    (device-event timing, max over ranks, end-to-end leg with pinned host inputs, one JSON line)."""
+    import torch
+    import torch.distributed as tdist
+
+    from dynpy_b200 import dist, ops, qrax, synth
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    rank, world, local = dist.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    F = wl["frames"] if args.frames is None else args.frames
+    if wl["kind"] == "qr":
+        S = wl["nuclei"]  # per GPU: weak scaling, every rank owns its own nuclei (cfg4 shards 1e5 nuclei over 8 GPUs)
+        base = synth.efg_series(256, F, seed=wl["seed"] + rank, device=dev)
+        data = base.repeat(S // 256, 1, 1).contiguous()
+        data += 1e-3 * torch.randn_like(data)
+        units_rank, unit, alg_bytes, scaling = float(S) * F, "nucleus-frames/s", 48.0, "weak"
+        tdev = torch.arange(F, device=dev, dtype=torch.float64) * 0.029
+        M = ops.fft_length(F)
+
+        def step(src):
+            spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
+            ops.qr_efg_to_spectrum(src, M=M, spectrum=spec)
+            dist.allreduce_sum_(spec)
+            acf = ops.ifft_acf(spec, F, 1.0 / (float(M) * F * S * world))[[2, 1, 0, 1, 2]].contiguous()
+            g, giso = qrax.spectral_dens(tdev, acf, "cartwright")
+            return acf, qrax.relaxation(g, giso, "127I")
+        metric = "nucleus-frames/s (quadrupolar ACFs + rates)"
+    else:
+        nmol = wl["nmol"]
+        box = synth.methane_box(nmol, seed=wl["seed"]).to(dev)
+        data = box.trajectory(F + 1, chunk=2048)
+        mol_atoms = torch.arange(nmol * 5, dtype=torch.int32, device=dev).reshape(nmol, 5)
+        mass = torch.tensor([12.010635561280681] + [1.0079407573975143] * 4, dtype=torch.float64, device=dev)
+        axis_atoms = torch.stack([mol_atoms[:, 0], mol_atoms[:, 1], mol_atoms[:, 0], mol_atoms[:, 2]], 1).contiguous()
+        L = box.celldm
+        lo, hi = dist.shard_range(nmol, rank, world)
+        units_rank, unit, alg_bytes, scaling = float(hi - lo) * F, "molecule-frames/s", 120.0, "strong"
+        tdev = torch.arange(1, F + 1, device=dev, dtype=torch.float64) * 0.001
+        M = ops.fft_length(F)
+
+        def step(src):
+            J, _, _ = ops.sr_angmom(src, mol_atoms[lo:hi].contiguous(), mass, axis_atoms[lo:hi].contiguous(), 0, (L, L, L),
+                                    1000.0, want_omega=False, want_axes=False)
+            spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
+            for c in range(3):
+                ops.wk_acf_sum(J[:, c, :].contiguous(), pack_real_pairs=True, M=M, spectrum=spec[c])
+            dist.allreduce_sum_(spec)
+            acf = ops.ifft_acf(spec, F, 1.0 / (float(M) * F * nmol))
+            return acf, ops.simpson(acf, tdev, "cartwright").cpu()
+        metric = "molecule-frames/s (spin-rotation ACFs + rate)"
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        e1.synchronize()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        return float(ms.item()) / steps, out
+
+    for _ in range(args.warmup):
+        step(data)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, _ = timed(lambda: step(data), args.steps)
+    clocks = sampler.stop() if sampler else None
+    host = torch.empty(data.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(data)
+    staging = torch.empty_like(data)
+    host_out = torch.empty((5 if wl["kind"] == "qr" else 3, F), dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        staging.copy_(host, non_blocking=True)
+        acf, r = step(staging)
+        host_out.copy_(acf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return r
+
+    e2e_step()
+    ms_e2e, _ = timed(e2e_step, max(1, min(args.steps, 3)))
+    if rank != 0:
+        dist.shutdown()
+        return
+    hbm, how = peaks()
+    total = units_rank * (world if scaling == "weak" else 1.0)
+    if scaling == "strong":
+        total = float(wl["nmol"]) * F
+    line = {"metric": metric, "value": total / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames": F, "fft_length": M,
+                       "l2": "inputs larger than L2 (%.2f GB per rank); no flush" % (data.numel() * 8 / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(data.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8)},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg_bytes * units_rank / (ms_step * 1e-3) / 1e9,
+                         "peak": hbm, "unit": "GB/s", "frac": alg_bytes * units_rank / (ms_step * 1e-3) / 1e9 / hbm,
+                         "traffic": None, "peak_source": how, "algorithmic_bytes_per_unit": alg_bytes}}
+    dist.shutdown()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,7 +472,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("kind") in ("qr", "sr"):
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for the dipolar "
+                                  "workloads (the headline metric) only"}))
+            return
+        other_arm(args, wl)
+    elif args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
         reference_arm(args, wl)
