@@ -117,12 +117,16 @@ __device__ __forceinline__ void st_stream(cd* p, cd v) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
-// threads per CTA of the column kernel: 512 (one CTA per SM, 16 warps running the same straight-line code
-// close together, which is what keeps the instruction caches effective); 128 x 3 CTAs for M1 = 64, whose
-// 32-point halves need 168 registers
+// threads per CTA of the column kernel: 256 x 2 CTAs per SM (8 warps running the same straight-line code
+// close together keep the instruction caches effective: 128 x 4 lost 12 %; two independent CTAs overlap
+// their load and compute phases: 512 x 1 lost 5 %); 128 x 3 CTAs for M1 = 64, whose 32-point halves need
+// 168 registers
+#ifndef TPC_NT
+#define TPC_NT 256
+#endif
 template <int M1> struct TpcShape {
-    static constexpr int NT = M1 >= 64 ? 128 : 512;
-    static constexpr int PER_SM = M1 >= 64 ? 3 : 1;
+    static constexpr int NT = M1 >= 64 ? 128 : TPC_NT;
+    static constexpr int PER_SM = M1 >= 64 ? 3 : 512 / TPC_NT;
 };
 
 template <int H> struct ColCodelets;
