@@ -253,3 +253,47 @@ def test_dd_fast_path_matches_generic_engine(ops, monkeypatch):
         out[path] = ops.ifft_acf(spec, F, 1.0 / (float(spec.shape[1]) * F)).cpu().numpy()
     for c in range(7):
         assert nerr(out["v2"][c], out["v1"][c]) < 1e-12
+
+
+def test_dd_full_size_properties(ops):
+    """cfg2 frame count (1e5 frames, M = 204800), thousands of pairs: size-independent properties of the fused
+    dipolar path — (1) the accumulated spectrum is additive over disjoint pair sets whatever the batching,
+    (2) lag 0 of every summed ACF equals the directly computed mean square of its series (Parseval), with the
+    series formed by independent torch code (27-image-free nearest image via rounding, angle-free Y2m)."""
+    from dynpy_b200 import synth
+    F = 100000
+    box = synth.water_box(32, seed=2).to("cuda")
+    hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
+    L = box.celldm
+    w = ops.wrap(box.trajectory(F, chunk=4096, atom_mask=hidx), L)
+    i, j = np.triu_indices(64, k=1)
+    i, j = i[:1501], j[:1501]           # odd count: the last pair-pair has one member
+    pi, pj = dev(i, torch.int32), dev(j, torch.int32)
+    cell = (L, L, L)
+    whole = ops.dd_pairs_to_spectrum(w, pi, pj, cell, ws_budget=4 << 30)
+    M = whole.shape[1]
+    assert M == 204800
+    part = ops.dd_pairs_to_spectrum(w, pi[:700], pj[:700], cell, ws_budget=300 << 20)
+    part = ops.dd_pairs_to_spectrum(w, pi[700:], pj[700:], cell, spectrum=part, ws_budget=1 << 30)
+    scale = whole.abs().amax(dim=1, keepdim=True)
+    assert float(((whole - part).abs() / scale).max()) < 1e-12
+    G0 = ops.ifft_acf(whole, F, 1.0 / (float(M) * F))[:, 0].cpu().numpy()
+    # independent evaluation of sum_pairs mean_t |series|^2
+    ref = np.zeros(7)
+    for s0 in range(0, len(i), 256):
+        a = w[torch.as_tensor(i[s0:s0 + 256], device="cuda")]
+        b = w[torch.as_tensor(j[s0:s0 + 256], device="cuda")]
+        d = a - b
+        d = d - L * torch.round(d / L)
+        r2 = (d * d).sum(dim=1)
+        r3 = r2 ** -1.5
+        x, y, z = d[:, 0], d[:, 1], d[:, 2]
+        y20 = 0.25 * np.sqrt(5 / np.pi) * (3 * z * z / r2 - 1)
+        y21sq = (0.5 * np.sqrt(15 / (2 * np.pi))) ** 2 * z * z * (x * x + y * y) / r2 ** 2
+        y22sq = (0.25 * np.sqrt(15 / (2 * np.pi))) ** 2 * (x * x + y * y) ** 2 / r2 ** 2
+        kf = 4 * np.pi / 5
+        dr3 = r3 - r3.mean(dim=1, keepdim=True)
+        for c, v in enumerate((y20 ** 2, y21sq, y22sq, dr3 ** 2, kf * r3 ** 2 * y20 ** 2, kf * r3 ** 2 * y21sq,
+                               kf * r3 ** 2 * y22sq)):
+            ref[c] += float(v.mean(dim=1).sum())
+    np.testing.assert_allclose(G0, ref, rtol=1e-10)
