@@ -42,6 +42,9 @@ SIGNATURES = {
     "dynpy_dd_pairs_ragged_to_acf_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, i64, p, i64, p]),
     "dynpy_sr_angmom_f64": (i32, [p, p, i64, i64, p, i64, i32, p, p, i32, f64, f64, f64, f64, p, p, p, p]),
     "dynpy_simpson_f64": (i32, [p, p, i64, i32, i64, i32, p, p]),
+    "dynpy_dft_workspace_bytes": (i64, [i64]),
+    "dynpy_dft_f64": (i32, [p, p, i64, i64, p, i64, p, i64, p]),
+    "dynpy_cutoff_bounds_f64": (i32, [p, i64, i32, i64, i32, f64, p, p]),
     "dynpy_parse_md_blocks_host": (i32, [C.c_char_p, i64, i32, i32, p, i64, f64, p, p, i32]),
 }
 

@@ -610,5 +610,36 @@ int dynpy_simpson_f64(const double* y, const double* x, int64_t n, int n_cols, i
     return DYNPY_OK;
 }
 
+// ------------------------------------------------------------------------------------------ J(omega)
+int64_t dynpy_dft_workspace_bytes(int64_t n) { return n >= 1 ? dft_workspace_bytes(n) : 0; }
+
+int dynpy_dft_f64(const double* re, const double* im, int64_t n_series, int64_t n, double* out, int64_t n_out,
+                  void* ws, int64_t ws_bytes, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!re || !out || !ws || n_series < 0 || n < 1 || n >= ((int64_t)1 << 30) || n_out < 0 || n_out > n) {
+        set_error("dynpy_dft_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    if (n_series == 0 || n_out == 0) return DYNPY_OK;
+    return dft_run(re, im, n_series, n, (cd*)out, n_out, ws, ws_bytes, d->n_sm, st);
+}
+
+int dynpy_cutoff_bounds_f64(const double* y, int64_t n, int n_cols, int64_t col_stride, int window, double tol,
+                            int64_t* bounds, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || !bounds || n < 1 || n_cols < 0 || col_stride < n || window < 1 || !(tol >= 0.0)) {
+        set_error("dynpy_cutoff_bounds_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_cutoff_bounds(y, n, n_cols, col_stride, window, tol, (i64*)bounds, d->n_sm, st), "cutoff bounds");
+    return DYNPY_OK;
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

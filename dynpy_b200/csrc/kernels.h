@@ -36,6 +36,13 @@ cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const 
 cudaError_t launch_simpson(const double* y, const double* x, i64 n, int n_cols, i64 col_stride, int mode,
                            double* out, cudaStream_t st);
 
+// finite-frequency spectral densities (spectral.cu)
+i64 dft_workspace_bytes(i64 n);
+int dft_run(const double* re, const double* im, i64 n_series, i64 n, cd* out, i64 n_out, void* ws, i64 ws_bytes,
+            int n_sm, cudaStream_t st);
+cudaError_t launch_cutoff_bounds(const double* y, i64 n, int n_cols, i64 col_stride, int window, double tol,
+                                 i64* bounds, int n_sm, cudaStream_t st);
+
 // dipolar fast path (dd2.cu): warp-autonomous fused column kernel + row kernel v2
 bool dd2_supported(i64 M);
 i64 dd2_workspace_bytes(i64 M, i64 N, i64 items);

@@ -76,12 +76,62 @@ def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True):
     return G, hit > 0, n_spins, info
 
 
-def spec_dens_extr_narr(time, G, simpson_mode="cartwright"):
-    """ddrax.py:186-222 (cutoff=False): j_2m = 2*simpson(G_2m, x=time); <F^2_m> = G_2m(0); tau's.
+J_COLUMNS = [r'$\omega$', r'$log(\omega)$', r'$\omega^{\\frac{1}{2}}$', r'$J_{0}(\omega)$', r'$J_{1}(\omega)$',
+             r'$J_{2}(\omega)$']
 
-    time [n] and G [7,n] are device tensors (rows in G_COLUMNS order); returns a dict of floats."""
+
+def fourier_T(f):
+    """ddrax.py:169-173: np.fft.fft(f)[range(n//2)] for series of ANY length, on the device.
+    f: real tensor [n] or [S, n] (cuda) -> complex128 [n//2] / [S, n//2]."""
+    one = f.dim() == 1
+    F = ops.dft(f.contiguous(), n_out=f.shape[-1] // 2)
+    return F[0] if one else F
+
+
+def fourier_freq(t):
+    """ddrax.py:174-178: np.fft.fftfreq(n, dt)[range(n//2)] with dt = t[1] - t[0] (host array in, host array out;
+    numpy forms k * (1/(n*dt)), so do we)."""
+    t = np.asarray(t, dtype=np.float64)
+    n = len(t)
+    val = 1.0 / (n * (t[1] - t[0]))
+    return np.arange(0, n // 2, dtype=int) * val
+
+
+def spec_dens(time, G):
+    """ddrax.py:178-184: finite-frequency spectral densities J_m(omega) = FFT(G_2m)[:n//2] on the frequency
+    grid of the ACF.  time [n], G [7, n] device tensors (rows in G_COLUMNS order) -> DataFrame with the
+    reference's columns (omega, log10 omega, sqrt omega, J_0, J_1, J_2; the J's complex)."""
+    import pandas as pd
+    freq = fourier_freq(time.cpu().numpy())
+    Jw = fourier_T(G[4:7].contiguous()).cpu().numpy()
+    with np.errstate(divide='ignore'):
+        logf = np.log10(freq)
+    return pd.DataFrame({J_COLUMNS[0]: freq, J_COLUMNS[1]: logf, J_COLUMNS[2]: np.sqrt(freq),
+                         J_COLUMNS[3]: Jw[0], J_COLUMNS[4]: Jw[1], J_COLUMNS[5]: Jw[2]})
+
+
+def spec_dens_extr_narr(time, G, simpson_mode="cartwright", dt=None, cutoff=False, cutoff_tol=1e-3):
+    """ddrax.py:186-222: j_2m = 2*simpson(G_2m, x=time) (or dx=dt); <F^2_m> = G_2m(0); tau's.
+
+    cutoff=True integrates only up to the first lag whose trailing 100-point mean of G/G(0) is within
+    cutoff_tol of zero; as in the reference the bound found for the LAST column (G_22) is applied to all
+    three columns (the loop variable `l` is read after the loop, ddrax.py:200).
+    time [n] and G [7,n] are device tensors (rows in G_COLUMNS order); returns a dict of floats
+    (plus 'bounds' when cutoff)."""
     y = G[4:7].contiguous()
-    j = (2.0 * ops.simpson(y, time.contiguous(), simpson_mode)).cpu().numpy()
+    extra = {}
+    if cutoff:
+        bounds = ops.cutoff_bounds(y, 100, cutoff_tol).tolist()
+        b = int(bounds[-1])
+        if b < 1:
+            raise ValueError("cutoff bound %d leaves no samples to integrate" % b)
+        j = (2.0 * ops.simpson(y, time.contiguous(), simpson_mode, n=b)).cpu().numpy()
+        extra['bounds'] = [int(v) for v in bounds]
+    else:
+        x = time.contiguous()
+        if dt:
+            x = torch.arange(y.shape[1], dtype=torch.float64, device=y.device) * float(dt)
+        j = (2.0 * ops.simpson(y, x, simpson_mode)).cpu().numpy()
     f = G[4:7, 0].cpu().numpy()
     g = {'$j_{2,0}$': float(j[0]), '$j_{2,1}$': float(j[1]), '$j_{2,2}$': float(j[2])}
     g[r'$\langle F^{2}_{0}\rangle$'] = float(f[0])
@@ -92,20 +142,56 @@ def spec_dens_extr_narr(time, G, simpson_mode="cartwright"):
     g[r'$\tau_{1}$'] = g['$j_{2,1}$'] / float(f[1])
     g[r'$\tau_{2}$'] = g['$j_{2,2}$'] / float(f[2])
     g[r'$\tau_{c}$'] = (g[r'$\tau_{1}$'] + g[r'$\tau_{2}$']) / 2
+    g.update(extra)
     return g
 
 
-def dipolar(spec_dens, symbol1, symbol2='H'):
-    """ddrax.py:224-274, extreme-narrowing branch (the only one the CLI reaches)."""
+def finite_freq_j(J, larmor_freq=25):
+    """ddrax.py:249-262: J_m at the Larmor frequency by a straight line in sqrt(omega) through rows 1 and 2 of
+    the spec_dens table: j0 ~ J_0(w0), j02 ~ J_0(2 w0), j1 ~ J_1(w0), j2 ~ J_2(2 w0), w0 = larmor_freq * 1e6.
+    Evaluated exactly as written there: intercept MINUS slope * sqrt(w0), with the signed fitted slope."""
+    omega_0 = larmor_freq * 1e6
+    sq = np.real(np.asarray(J[J_COLUMNS[2]]))
+
+    def line(col):
+        y = np.real(np.asarray(J[col]))
+        m = (y[2] - y[1]) / (sq[2] - sq[1])
+        return m, y[2] - m * sq[2]
+
+    m0, b0 = line(J_COLUMNS[3])
+    m1, b1 = line(J_COLUMNS[4])
+    m2, b2 = line(J_COLUMNS[5])
+    return dict(j0=b0 - m0 * np.sqrt(omega_0), j02=b0 - m0 * np.sqrt(2 * omega_0), j1=b1 - m1 * np.sqrt(omega_0),
+                j2=b2 - m2 * np.sqrt(2 * omega_0))
+
+
+def dipolar(spec_dens, symbol1, symbol2='H', extr_narr=True, single_J=False, larmor_freq=25, J=None):
+    """ddrax.py:224-274.  extr_narr=True is the branch the CLI reaches.  The other two branches cannot run in
+    the reference as written (single_J: `symbol` undefined at :237; extr_narr=False: `J`, `tc`, `f` undefined
+    at :249/:274) — here single_J returns the one-row table the reference tries to build, indexed by symbol1,
+    and extr_narr=False takes the spec_dens() table as `J` (NameError without it, like the reference) and
+    returns (R, None, None)."""
     s = nuc[symbol1]['I']
     gamma1 = nuc[symbol1]['gamma']
     gamma2 = nuc[symbol2]['gamma']
     C_d = (MU_0 / (4 * math.pi)) ** 2 * (gamma1 ** 2) * (gamma2 ** 2) * (HBAR ** 2)
     s_const = s * (s + 1)
     au_m = 5.29177e-11
-    j0 = j1 = j2 = float(np.mean([spec_dens['$j_{2,0}$'], spec_dens['$j_{2,1}$'], spec_dens['$j_{2,2}$']]))
-    tc = spec_dens['$\\tau_{c}$']
-    f = C_d * s_const * au_m ** (-6) * spec_dens[r'$\langle F^{2}_{0}\rangle$']
+    tc = f = None
+    if single_J:
+        import pandas as pd
+        j1 = j2 = spec_dens
+        R = np.real(C_d * s_const * (j1 + (4 * j2)) * au_m ** (-6) * 1e-12)
+        return pd.DataFrame({'$\\frac{1}{T_{1}}$': R}, index=[symbol1])
+    elif extr_narr:
+        j0 = j1 = j2 = float(np.mean([spec_dens['$j_{2,0}$'], spec_dens['$j_{2,1}$'], spec_dens['$j_{2,2}$']]))
+        tc = spec_dens['$\\tau_{c}$']
+        f = C_d * s_const * au_m ** (-6) * spec_dens[r'$\langle F^{2}_{0}\rangle$']
+    else:
+        if J is None:
+            raise NameError("name 'J' is not defined (ddrax.py:249): pass the spec_dens() table as J=")
+        ff = finite_freq_j(J, larmor_freq)
+        j0, j1, j2 = ff['j0'], ff['j1'], ff['j2']
     if symbol1 == symbol2:
         R = float(np.real(C_d * s_const * (j1 + (4 * j2)) * au_m ** (-6) * 1e-12))
     else:

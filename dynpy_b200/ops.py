@@ -297,16 +297,61 @@ def sr_angmom(pos, mol_atoms, mass, axis_atoms, axis_rule, cell, inv_dt, vel=Non
 SIMPSON_MODES = {"cartwright": 0, "avg": 1}
 
 
-def simpson(y, x, mode="cartwright"):
-    """scipy.integrate.simpson(y[c], x=x) for every row c of y [cols, n] -> tensor [cols]."""
+def simpson(y, x, mode="cartwright", n=None):
+    """scipy.integrate.simpson(y[c, :n], x=x[:n]) for every row c of y [cols, len] -> tensor [cols]."""
     lib = _lib.load()
     y = _chk(y, torch.float64, "y")
     x = _chk(x, torch.float64, "x")
     if y.dim() == 1:
         y = y[None]
-    cols, n = y.shape
+    cols, stride = y.shape
+    n = stride if n is None else int(n)
+    if n < 1 or n > stride or x.numel() < n:
+        raise _lib.DynpyError("simpson: n = %d outside the series (length %d)" % (n, stride))
     out = torch.empty(cols, dtype=torch.float64, device=y.device)
     with torch.cuda.device(y.device):
-        rc = lib.dynpy_simpson_f64(y.data_ptr(), x.data_ptr(), n, cols, n, SIMPSON_MODES[mode], out.data_ptr(), _stream())
+        rc = lib.dynpy_simpson_f64(y.data_ptr(), x.data_ptr(), n, cols, stride, SIMPSON_MODES[mode], out.data_ptr(),
+                                   _stream())
     _lib.check(rc, "dynpy_simpson_f64")
+    return out
+
+
+# ------------------------------------------------------------------------------ J(omega)
+def dft(re, im=None, n_out=None):
+    """numpy.fft.fft along the last axis of re (+ i im) [S, n] for ANY n -> complex128 [S, n_out]."""
+    lib = _lib.load()
+    re = _chk(re, torch.float64, "re")
+    if re.dim() == 1:
+        re = re[None]
+    S, n = re.shape
+    if im is not None:
+        im = _chk(im, torch.float64, "im")
+        if im.dim() == 1:
+            im = im[None]
+        assert im.shape == re.shape
+    n_out = n if n_out is None else int(n_out)
+    out = torch.empty((S, n_out, 2), dtype=torch.float64, device=re.device)
+    if out.numel() == 0:
+        return torch.view_as_complex(out)
+    with torch.cuda.device(re.device):
+        wsb = int(lib.dynpy_dft_workspace_bytes(n))
+        ws = workspace(re.device, wsb)
+        rc = lib.dynpy_dft_f64(re.data_ptr(), im.data_ptr() if im is not None else None, S, n, out.data_ptr(), n_out,
+                               ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dynpy_dft_f64")
+    return torch.view_as_complex(out)
+
+
+def cutoff_bounds(y, window=100, tol=1e-3):
+    """Per row of y [cols, n]: first index i < n-1 whose trailing `window`-mean of y/y[0] is within tol
+    of zero, else n-1 -> int64 tensor [cols] (device)."""
+    lib = _lib.load()
+    y = _chk(y, torch.float64, "y")
+    if y.dim() == 1:
+        y = y[None]
+    cols, n = y.shape
+    out = torch.empty(cols, dtype=torch.int64, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = lib.dynpy_cutoff_bounds_f64(y.data_ptr(), n, cols, n, int(window), float(tol), out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_cutoff_bounds_f64")
     return out

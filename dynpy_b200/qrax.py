@@ -52,9 +52,22 @@ def efg_acf_mean(efg: torch.Tensor, shard=True):
     return acf[[2, 1, 0, 1, 2]].contiguous()
 
 
-def spectral_dens(time, f, simpson_mode="cartwright"):
-    """qrax.py:169-201 (cutoff=False): g_2m = simpson(f_2m, x=time); g_iso = mean. Device tensors in."""
-    g = ops.simpson(f.contiguous(), time.contiguous(), simpson_mode).cpu().numpy()
+def spectral_dens(time, f, simpson_mode="cartwright", dt=None, cutoff=False, cutoff_tol=1e-3):
+    """qrax.py:169-201: g_2m = simpson(f_2m, x=time) (or dx=dt); g_iso = mean. Device tensors in.
+    cutoff=True integrates up to the first lag whose trailing 100-point mean of f/f(0) is within cutoff_tol
+    of zero — the bound of the LAST column (f_22) for all five, as the reference's leaked loop variable does
+    (qrax.py:184)."""
+    y = f.contiguous()
+    if cutoff:
+        b = int(ops.cutoff_bounds(y, 100, cutoff_tol)[-1])
+        if b < 1:
+            raise ValueError("cutoff bound %d leaves no samples to integrate" % b)
+        g = ops.simpson(y, time.contiguous(), simpson_mode, n=b).cpu().numpy()
+    else:
+        x = time.contiguous()
+        if dt:
+            x = torch.arange(y.shape[1], dtype=torch.float64, device=y.device) * float(dt)
+        g = ops.simpson(y, x, simpson_mode).cpu().numpy()
     return [float(x) for x in g], float(np.mean(g))
 
 

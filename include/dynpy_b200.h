@@ -176,6 +176,21 @@ int dynpy_sr_angmom_f64(const double* pos, const double* vel, int64_t n_atoms, i
 int dynpy_simpson_f64(const double* y, const double* x, int64_t n, int n_cols, int64_t col_stride,
                       int mode, double* out, dynpy_stream_t stream);
 
+/* ---- finite-frequency spectral densities ----------------------------------------------------------
+ * numpy.fft.fft of ARBITRARY length n, as ddrax.fourier_T applies it to the G_2m columns of avg-acf
+ * (ddrax.py:169-184): out[s][k] = sum_j (re[s][j] + i im[s][j]) exp(-2 pi i j k / n), k < n_out <= n;
+ * im may be NULL (real series).  out is interleaved complex [n_series][n_out][2].
+ * ws: dynpy_dft_workspace_bytes(n). */
+int64_t dynpy_dft_workspace_bytes(int64_t n);
+int dynpy_dft_f64(const double* re, const double* im, int64_t n_series, int64_t n, double* out,
+                  int64_t n_out, void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+/* Integration bound of spec_dens_extr_narr / spectral_dens with cutoff=True (ddrax.py:188-198,
+ * qrax.py:172-182): bounds[col] = first i < n-1 whose trailing `window`-point mean of y/y[0] is within
+ * `tol` of zero (pandas rolling(window).mean() + numpy.isclose(., 0, atol=tol)), else n-1.
+ * y[col*col_stride + k]; bounds: device int64 [n_cols]. */
+int dynpy_cutoff_bounds_f64(const double* y, int64_t n, int n_cols, int64_t col_stride, int window,
+                            double tol, int64_t* bounds, dynpy_stream_t stream);
+
 /* ---- trajectory ingestion (HOST function; no GPU needed) -----------------------------------------
  * replaces the text handling of parseMD.parse_xyz / parse_tinker_md (parseMD.py:177-278):
  * blocks of  <header_lines> lines + nat atom lines  "[cols...] sym x y z [cols...]";

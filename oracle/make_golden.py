@@ -131,12 +131,55 @@ def _leaf_vectors():
     print("golden: leaf_vectors.npz", sorted(out)[:6], "...")
 
 
+def _specdens_vectors():
+    """Outputs of the reference's finite-frequency / cutoff / dx integration code (ddrax.spec_dens,
+    ddrax.spec_dens_extr_narr, qrax.spectral_dens) on seeded synthetic ACF tables -> specdens_vectors.npz.
+    The even-n Simpson values are those of the scipy importable here (see the `scipy` entry)."""
+    import numpy as np
+    import pandas as pd
+    import scipy
+    refshim.import_reference()
+    import qrax, ddrax
+    rng = np.random.default_rng(17)
+    out = {"scipy": np.array(scipy.__version__)}
+    gcols = ['$G_{2,0}$', '$G_{2,1}$', '$G_{2,2}$']
+    fcols = ['$f_{2,-2}$', '$f_{2,-1}$', '$f_{2,0}$', '$f_{2,1}$', '$f_{2,2}$']
+    jcols = [r'$\omega$', r'$log(\omega)$', r'$\omega^{\\frac{1}{2}}$', r'$J_{0}(\omega)$', r'$J_{1}(\omega)$', r'$J_{2}(\omega)$']
+    # n: even / odd / prime / too short for one window; decay and noise chosen so that the cutoff bound
+    # falls inside the table for some columns and at the end for others
+    for k, (n, tau, noise) in enumerate([(1000, 0.05, 2e-4), (777, 0.3, 1e-3), (1009, 0.02, 5e-3), (60, 0.01, 1e-4)]):
+        t = 0.4 + 0.002 * np.arange(n)            # avg-acf.csv time does not start at 0 (SURVEY app. B4)
+        amp = rng.uniform(0.5, 2.0, 5)
+        taus = tau * rng.uniform(0.6, 1.6, 5)
+        Y = amp[:, None] * np.exp(-(t - t[0])[None, :] / taus[:, None]) * np.cos(7.0 * (t - t[0]))[None, :] \
+            + noise * rng.normal(size=(5, n))
+        out["t%d" % k] = t; out["Y%d" % k] = Y
+        dd = pd.DataFrame({"time": t, gcols[0]: Y[0], gcols[1]: Y[1], gcols[2]: Y[2]})
+        qr = pd.DataFrame({"time": t, "symbol": "I", **{c: Y[i] for i, c in enumerate(fcols)}})
+        with np.errstate(divide="ignore"):
+            J = ddrax.spec_dens(dd)
+        out["J%d" % k] = np.stack([J[c].to_numpy().astype(np.complex128) for c in jcols])
+        for tag, kw in (("plain", {}), ("dt", dict(dt=0.002)), ("cut", dict(cutoff=True)),
+                        ("cut2", dict(cutoff=True, cutoff_tol=2e-2))):
+            g = ddrax.spec_dens_extr_narr(dd, **kw)
+            out["dd_%s%d" % (tag, k)] = np.array([g['$j_{2,0}$'], g['$j_{2,1}$'], g['$j_{2,2}$'], g[r'$\tau_{c}$']],
+                                                  dtype=np.float64)
+            h = qrax.spectral_dens(qr, **kw)
+            out["qr_%s%d" % (tag, k)] = np.array([h[c] for c in ['$g_{2,-2}$', '$g_{2,-1}$', '$g_{2,0}$', '$g_{2,1}$',
+                                                                 '$g_{2,2}$', '$g_{iso}$']], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "specdens_vectors.npz"), **out)
+    print("golden: specdens_vectors.npz", len(out), "arrays")
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
     if "--leaf-only" in sys.argv:
         return _leaf_vectors()
+    if "--specdens-only" in sys.argv:
+        return _specdens_vectors()
     _leaf_vectors()
+    _specdens_vectors()
     # the reference's own (only) known-answer set
     ref_nb = os.path.join(refshim.REFERENCE, "notebooks")
     dst = os.path.join(GOLD, "reference_iodide")

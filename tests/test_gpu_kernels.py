@@ -297,3 +297,92 @@ def test_dd_full_size_properties(ops):
                                kf * r3 ** 2 * y22sq)):
             ref[c] += float(v.mean(dim=1).sum())
     np.testing.assert_allclose(G0, ref, rtol=1e-10)
+
+
+# ---------------------------------------------------------------- J(omega) / cutoff
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 60, 316, 777, 1000, 1009, 4096, 65536, 99991, 100000])
+def test_dft_any_length_vs_numpy(ops, n):
+    rng = np.random.default_rng(n)
+    re = rng.normal(size=(2, n))
+    im = rng.normal(size=(2, n))
+    got = ops.dft(dev(re), dev(im)).cpu().numpy()
+    ref = np.fft.fft(re + 1j * im, axis=1)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1.0) * max(1.0, np.log2(n + 1))
+    # real input, first half only (the shape ddrax.fourier_T asks for)
+    got = ops.dft(dev(re[0]), n_out=n // 2).cpu().numpy()
+    ref = np.fft.fft(re[0])[:n // 2]
+    assert got.shape == (1, n // 2)
+    if n >= 2:
+        assert np.abs(got[0] - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1.0) * max(1.0, np.log2(n + 1))
+
+
+def test_dft_known_answers(ops):
+    n = 1000
+    j = np.arange(n)
+    x = np.cos(2 * np.pi * 37 * j / n)
+    X = ops.dft(dev(x)).cpu().numpy()[0]
+    want = np.zeros(n, dtype=complex); want[37] = want[n - 37] = n / 2
+    assert np.abs(X - want).max() < 1e-10
+    X = ops.dft(dev(np.ones(997))).cpu().numpy()[0]      # prime length, constant series
+    assert abs(X[0] - 997) < 1e-10 and np.abs(X[1:]).max() < 1e-10
+
+
+def test_cutoff_bounds_vs_oracle(ops):
+    g = np.load(os.path.join(GOLDEN, "specdens_vectors.npz"))
+    for k in range(4):
+        Y = g["Y%d" % k]
+        for tol in (1e-3, 2e-2, 0.3):
+            got = ops.cutoff_bounds(dev(Y), 100, tol).cpu().numpy()
+            ref = np.array([orc.cutoff_bound(y, 100, tol) for y in Y])
+            np.testing.assert_array_equal(got, ref)
+    y = np.ones(300); y[150:] = 0.0
+    assert ops.cutoff_bounds(dev(y)).tolist() == [249]
+    assert ops.cutoff_bounds(dev(y), 100, 0.5).tolist() == [199]
+    assert ops.cutoff_bounds(dev(y), 7, 0.0).tolist() == [156]
+    rng = np.random.default_rng(3)
+    Y = rng.normal(size=(6, 20000)) * np.exp(-np.arange(20000) / 900.0) + 1e-4
+    Y[:, 0] = 1.0
+    got = ops.cutoff_bounds(dev(Y), 100, 1e-3).cpu().numpy()
+    np.testing.assert_array_equal(got, [orc.cutoff_bound(y) for y in Y])
+
+
+def test_spectral_density_mirrors_vs_reference_vectors(ops):
+    """ddrax.spec_dens / spec_dens_extr_narr(dt|cutoff) / dipolar(extr_narr=False) and
+    qrax.spectral_dens(dt|cutoff) of the product against the reference's outputs (specdens_vectors.npz)."""
+    from dynpy_b200 import ddrax, qrax
+    g = np.load(os.path.join(GOLDEN, "specdens_vectors.npz"))
+    for k in range(4):
+        t, Y = g["t%d" % k], g["Y%d" % k]
+        G = torch.zeros((7, len(t)), dtype=torch.float64, device="cuda")
+        G[4:7] = dev(Y[:3])
+        J = ddrax.spec_dens(dev(t), G)
+        ref = g["J%d" % k]
+        assert list(J.columns) == ddrax.J_COLUMNS
+        np.testing.assert_allclose(J[ddrax.J_COLUMNS[0]].to_numpy(), ref[0].real, rtol=1e-15)
+        np.testing.assert_allclose(J[ddrax.J_COLUMNS[2]].to_numpy(), ref[2].real, rtol=1e-15)
+        np.testing.assert_allclose(J[ddrax.J_COLUMNS[1]].to_numpy()[1:], ref[1].real[1:], rtol=1e-15)
+        for c in range(3):
+            got = J[ddrax.J_COLUMNS[3 + c]].to_numpy()
+            assert np.abs(got - ref[3 + c]).max() <= 1e-12 * np.abs(ref[3 + c]).max()
+        for tag, kw in (("plain", {}), ("dt", dict(dt=0.002)), ("cut", dict(cutoff=True)),
+                        ("cut2", dict(cutoff=True, cutoff_tol=2e-2))):
+            want = g["dd_%s%d" % (tag, k)]
+            e = ddrax.spec_dens_extr_narr(dev(t), G, "cartwright", **kw)
+            got = [e['$j_{2,0}$'], e['$j_{2,1}$'], e['$j_{2,2}$'], e[r'$\tau_{c}$']]
+            np.testing.assert_allclose(got, want, rtol=1e-10, err_msg="dd %s %d" % (tag, k))
+            wq = g["qr_%s%d" % (tag, k)]
+            q, qiso = qrax.spectral_dens(dev(t), dev(Y), "cartwright", **kw)
+            np.testing.assert_allclose(q + [qiso], wq, rtol=1e-10, err_msg="qr %s %d" % (tag, k))
+        if len(t) >= 100:
+            Jd = dict(sqrt_omega=J[ddrax.J_COLUMNS[2]].to_numpy(), J0=J[ddrax.J_COLUMNS[3]].to_numpy(),
+                      J1=J[ddrax.J_COLUMNS[4]].to_numpy(), J2=J[ddrax.J_COLUMNS[5]].to_numpy())
+            for s2 in ("1H", "13C"):
+                want = orc.dd_finite_freq(Jd, "1H", s2, larmor_freq=400)
+                R, tc, f = ddrax.dipolar(None, "1H", s2, extr_narr=False, larmor_freq=400, J=J)
+                assert tc is None and f is None
+                np.testing.assert_allclose(R, want["R"], rtol=1e-12)
+    with pytest.raises(NameError):
+        ddrax.dipolar(None, "1H", "1H", extr_narr=False)
+    one = ddrax.dipolar(2.5e-3, "1H", "1H", single_J=True)
+    assert list(one.index) == ["1H"] and one.shape == (1, 1)

@@ -157,3 +157,64 @@ def test_leaf_vectors_vs_reference():
     y20, y21, y22, r3, f0, f1, f2 = orc.dd_words(dx, dy, dz, dr)
     for got, nm in ((r3, "r-3"), (y20, "Y20"), (y21, "Y21"), (y22, "Y22"), (f0, "F20"), (f1, "F21"), (f2, "F22")):
         np.testing.assert_allclose(got, d["dd_" + nm], rtol=1e-14, atol=1e-16)
+
+
+# ---------------------------------------------------------------- J(omega) / cutoff / dx
+SPECDENS_CASES = 4
+
+
+def specdens_golden():
+    return np.load(os.path.join(GOLDEN, "specdens_vectors.npz"))
+
+
+def test_specdens_vectors_vs_reference():
+    g = specdens_golden()
+    for k in range(SPECDENS_CASES):
+        t, Y = g["t%d" % k], g["Y%d" % k]
+        J = orc.dd_spec_dens(t, Y[0], Y[1], Y[2])
+        ref = g["J%d" % k]
+        np.testing.assert_allclose(J["omega"], ref[0].real, rtol=1e-15)
+        np.testing.assert_allclose(J["sqrt_omega"], ref[2].real, rtol=1e-15)
+        assert np.isneginf(J["log_omega"][0]) and np.isneginf(ref[1].real[0])
+        np.testing.assert_allclose(J["log_omega"][1:], ref[1].real[1:], rtol=1e-15)
+        for c, nm in enumerate(("J0", "J1", "J2")):
+            np.testing.assert_allclose(J[nm], ref[3 + c], rtol=0, atol=1e-13 * np.abs(ref[3 + c]).max())
+        for tag, kw in (("plain", {}), ("dt", dict(dt=0.002)), ("cut", dict(cutoff=True)),
+                        ("cut2", dict(cutoff=True, cutoff_tol=2e-2))):
+            j, _ = orc.integrate_columns(t, Y[:3], **kw)
+            want = g["dd_%s%d" % (tag, k)]
+            np.testing.assert_allclose(2 * j, want[:3], rtol=1e-12, err_msg="dd %s %d" % (tag, k))
+            tau_c = 0.5 * (2 * j[1] / Y[1, 0] + 2 * j[2] / Y[2, 0])
+            np.testing.assert_allclose(tau_c, want[3], rtol=1e-12)
+            q, _ = orc.integrate_columns(t, Y, **kw)
+            wq = g["qr_%s%d" % (tag, k)]
+            np.testing.assert_allclose(q, wq[:5], rtol=1e-12, err_msg="qr %s %d" % (tag, k))
+            np.testing.assert_allclose(q.mean(), wq[5], rtol=1e-12)
+
+
+def test_cutoff_bound_semantics():
+    # the bound of the LAST column is the one applied to every column; short tables fall back to n-1
+    g = specdens_golden()
+    t, Y = g["t0"], g["Y0"]
+    _, b3 = orc.integrate_columns(t, Y[:3], cutoff=True)
+    _, b5 = orc.integrate_columns(t, Y, cutoff=True)
+    assert 99 <= b3[-1] < len(t) - 1 and 99 <= b5[-1] < len(t) - 1
+    assert len(set(b5)) > 1
+    assert orc.cutoff_bound(g["Y3"][0]) == len(g["t3"]) - 1
+    y = np.ones(300); y[150:] = 0.0
+    # trailing 100-mean first reaches <= 1e-3 when the window holds only zeros: i = 249
+    assert orc.cutoff_bound(y) == 249
+    assert orc.cutoff_bound(y, tol=0.5) == 199
+
+
+def test_finite_freq_formula_as_written():
+    # ddrax.py:249-262 evaluates  b - m*sqrt(omega0)  with m the fitted SLOPE (not its magnitude): for
+    # J(omega) = B + S sqrt(omega) the as-written result is B - S sqrt(omega0).  Restated literally.
+    w = np.arange(10) * 1.0e5
+    J = dict(sqrt_omega=np.sqrt(w), J0=3.0 - 2e-4 * np.sqrt(w) + 0j, J1=2.0 - 1e-4 * np.sqrt(w) + 0j,
+             J2=1.0 - 5e-5 * np.sqrt(w) + 0j)
+    r = orc.dd_finite_freq(J, larmor_freq=25)
+    np.testing.assert_allclose([r["j0"], r["j02"], r["j1"], r["j2"]],
+                               [3.0 + 2e-4 * 5e3, 3.0 + 2e-4 * np.sqrt(5e7), 2.0 + 1e-4 * 5e3, 1.0 + 5e-5 * np.sqrt(5e7)],
+                               rtol=1e-12)
+    assert r["R"] > 0 and r["zf"] > 0
