@@ -353,8 +353,9 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
         set_error("dynpy_pdist_ortho_f64: invalid arguments");
         return DYNPY_ERR_INVALID;
     }
-    if (n >= 2 && (!dx || !dy || !dz || !dr || !atom0 || !atom1 || !projection)) {
-        set_error("dynpy_pdist_ortho_f64: output arrays missing");
+    const bool count_only = !dx && !dy && !dz && !dr && !atom0 && !atom1 && !projection;
+    if (n >= 2 && !count_only && (!dx || !dy || !dz || !dr || !atom0 || !atom1 || !projection)) {
+        set_error("dynpy_pdist_ortho_f64: output arrays missing (pass all seven, or none for a count-only call)");
         return DYNPY_ERR_INVALID;
     }
     if (n >= 2 && (ws_bytes < dynpy_pdist_workspace_bytes(n) || !ws)) {
@@ -366,6 +367,20 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
     if (rc) return rc;
     DYNPY_CHECK(launch_pdist(ux, uy, uz, stride, n, a, b, c, (const i64*)index, dmax, dx, dy, dz, dr, (i64*)atom0,
                              (i64*)atom1, (i64*)projection, (i64*)count, (i64*)ws, st), "pdist_ortho");
+    return DYNPY_OK;
+}
+
+int dynpy_supercell_f64(const double* coords, int64_t n_atoms, int64_t n_frames, int64_t frame, double a, double* out,
+                        dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!coords || !out || n_atoms < 1 || n_frames < 1 || frame < 0 || frame >= n_frames) {
+        set_error("dynpy_supercell_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_supercell(coords, n_atoms, n_frames, frame, a, out, st), "supercell");
     return DYNPY_OK;
 }
 

@@ -18,6 +18,7 @@ cudaError_t launch_wrap(const double* x, double* out, i64 n, double L, int n_sm,
 cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i64 stride, i64 n, double a,
                          double b, double c, const i64* index, double dmax, double* dx, double* dy, double* dz,
                          double* dr, i64* a0, i64* a1, i64* prj, i64* count, i64* block_counts, cudaStream_t st);
+cudaError_t launch_supercell(const double* pos, i64 n, i64 F, i64 frame, double a, double* out, cudaStream_t st);
 cudaError_t launch_dd_words(const double* X, i64 A, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs,
                             i64 items, double a, double b, double c, double* Z, double* bias, cudaStream_t st);
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,

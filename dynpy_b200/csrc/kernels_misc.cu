@@ -85,6 +85,22 @@ k_pdist(const double* __restrict__ ux, const double* __restrict__ uy, const doub
     }
 }
 
+// neighbors._worker (neighbors.py:160-199): the 3x3x3 block of periodic images of one frame, image
+// p = 9 (i+1) + 3 (j+1) + (k+1), i, j, k in {-1, 0, 1}; super atom p * n + l sits at x_l + i*a (etc.)
+__global__ void k_supercell(const double* __restrict__ pos, i64 n, i64 F, i64 frame, double a, double* __restrict__ out) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // over 27 n
+    if (t >= 27 * n) return;
+    const int p = (int)(t / n);
+    const i64 l = t - (i64)p * n;
+    const int sh[3] = {p / 9 - 1, (p / 3) % 3 - 1, p % 3 - 1};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[(i64)d * 27 * n + t] = __dadd_rn(pos[(l * 3 + d) * F + frame], __dmul_rn((double)sh[d], a));
+}
+cudaError_t launch_supercell(const double* pos, i64 n, i64 F, i64 frame, double a, double* out, cudaStream_t st) {
+    k_supercell<<<(unsigned)((27 * n + 255) / 256), 256, 0, st>>>(pos, n, F, frame, a, out);
+    return cudaGetLastError();
+}
+
 // exclusive scan of block counts by one CTA; total -> *count
 __global__ void k_scan_counts(i64* __restrict__ v, i64 n, i64* __restrict__ count) {
     __shared__ i64 sh[1024];
@@ -122,6 +138,7 @@ cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i
     k_pdist<false><<<(unsigned)nblocks, 256, 0, st>>>(ux, uy, uz, stride, n, a, b, c, index, dmax2, npairs,
                                                      block_counts, dx, dy, dz, dr, a0, a1, prj);
     k_scan_counts<<<1, 1024, 0, st>>>(block_counts, nblocks, count);
+    if (!dx) return cudaGetLastError();  // count-only call: the caller sizes the outputs from *count
     k_pdist<true><<<(unsigned)nblocks, 256, 0, st>>>(ux, uy, uz, stride, n, a, b, c, index, dmax2, npairs,
                                                     block_counts, dx, dy, dz, dr, a0, a1, prj);
     return cudaGetLastError();

@@ -156,7 +156,8 @@ def wrap(x, L: float, out=None):
 
 
 def pdist_ortho(ux, uy, uz, a, b, c, index, dmax=8.0, stride=1):
-    """Bit-exact distances.pdist_ortho for one frame -> (dx, dy, dz, dr, atom0, atom1, projection)."""
+    """Bit-exact distances.pdist_ortho for one frame -> (dx, dy, dz, dr, atom0, atom1, projection).
+    Large frames are counted first so that the outputs are sized by the rows found, not by n(n-1)/2."""
     lib = _lib.load()
     for t, nm in ((ux, "ux"), (uy, "uy"), (uz, "uz")):
         if not t.is_cuda or t.dtype != torch.float64:
@@ -165,19 +166,38 @@ def pdist_ortho(ux, uy, uz, a, b, c, index, dmax=8.0, stride=1):
     n = index.numel()
     nn = n * (n - 1) // 2
     dev = index.device
-    f = [torch.empty(max(nn, 1), dtype=torch.float64, device=dev) for _ in range(4)]
-    g = [torch.empty(max(nn, 1), dtype=torch.int64, device=dev) for _ in range(3)]
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         wsb = int(lib.dynpy_pdist_workspace_bytes(n))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        rc = lib.dynpy_pdist_ortho_f64(ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), int(stride), n, float(a), float(b),
-                                       float(c), index.data_ptr(), float(dmax), f[0].data_ptr(), f[1].data_ptr(),
-                                       f[2].data_ptr(), f[3].data_ptr(), g[0].data_ptr(), g[1].data_ptr(),
-                                       g[2].data_ptr(), cnt.data_ptr(), ws.data_ptr(), wsb, _stream())
+        args = (ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), int(stride), n, float(a), float(b), float(c),
+                index.data_ptr(), float(dmax))
+        cap = nn
+        if nn > (1 << 20):
+            rc = lib.dynpy_pdist_ortho_f64(*args, None, None, None, None, None, None, None, cnt.data_ptr(), ws.data_ptr(),
+                                           wsb, _stream())
+            _lib.check(rc, "dynpy_pdist_ortho_f64 (count)")
+            cap = int(cnt.item())
+        f = [torch.empty(max(cap, 1), dtype=torch.float64, device=dev) for _ in range(4)]
+        g = [torch.empty(max(cap, 1), dtype=torch.int64, device=dev) for _ in range(3)]
+        rc = lib.dynpy_pdist_ortho_f64(*args, f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(), f[3].data_ptr(),
+                                       g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                       wsb, _stream())
     _lib.check(rc, "dynpy_pdist_ortho_f64")
     k = int(cnt.item())
     return tuple(t[:k] for t in f) + tuple(t[:k] for t in g)
+
+
+def supercell(coords, frame: int, a: float):
+    """[A,3,F] raw coords -> [3, 27A]: the 27 periodic images of frame index `frame` (neighbors._worker)."""
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    A, three, F = coords.shape
+    out = torch.empty((3, 27 * A), dtype=torch.float64, device=coords.device)
+    with torch.cuda.device(coords.device):
+        rc = lib.dynpy_supercell_f64(coords.data_ptr(), A, F, int(frame), float(a), out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_supercell_f64")
+    return out
 
 
 def topology_check(coords, rcov, bond_extra, expect, cell, dmax):

@@ -54,8 +54,12 @@ def bonded(two: dict, symbols, bond_extra: float = 0.45) -> np.ndarray:
 class Topology:
     """Molecules of one frame in the reference's numbering.
 
-    mol_rank[a] : molecule index inside the frame in networkx discovery order — isolated atoms
-                  first (atom order), then connected components ordered by their smallest atom.
+    mol_rank[a] : rank of atom a's connected component among ALL components of the frame (single atoms
+                  included), ordered by their smallest atom — networkx's connected_components order.
+    n_isolated  : number of unbonded atoms.  compute_molecule (universe.py:426-437) first numbers those
+                  0..n_isolated-1 and then overwrites them while walking connected_components (which yields
+                  single-node components too), so the number the reference ends up with for a molecule of a
+                  single frame is n_isolated + mol_rank (`frame_molecule_id`).
     groups      : list (by mol_rank) of atom-label tuples (ascending).
     """
 
@@ -78,16 +82,10 @@ class Topology:
         self.nat = nat
         self.symbols = list(symbols)
         self.mol_rank = np.full(nat, -1, dtype=np.int64)
+        self.n_isolated = int((deg == 0).sum())
         k = 0
-        for a in range(nat):
-            if deg[a] == 0:
-                self.mol_rank[a] = k
-                k += 1
-        self.n_isolated = k
         seen = {}
         for a in range(nat):
-            if deg[a] == 0:
-                continue
             r = find(a)
             if r not in seen:
                 seen[r] = k
@@ -99,6 +97,10 @@ class Topology:
             self.groups[self.mol_rank[a]].append(a)
         self.groups = [tuple(g) for g in self.groups]
         self.bonds = set(zip(bi.tolist(), bj.tolist()))
+
+    def frame_molecule_id(self, m):
+        """Number compute_molecule gives molecule(s) m when the universe holds this one frame."""
+        return self.n_isolated + m
 
     def formula(self, m: int) -> dict:
         out = {}
@@ -118,12 +120,10 @@ class Topology:
         return hit
 
     def molecule_id(self, frame_index: int, m: int, nframes: int) -> int:
-        """Global 'molecule' id the reference would assign (universe.py:426-437) for a topology
-        that is the same in every frame: all isolated atoms of all frames first, then components."""
-        if m < self.n_isolated:
-            return frame_index * self.n_isolated + m
-        n_multi = self.nmol - self.n_isolated
-        return nframes * self.n_isolated + frame_index * n_multi + (m - self.n_isolated)
+        """Global 'molecule' id the reference assigns (universe.py:426-437) in a universe of `nframes` frames
+        with this topology in every frame: numbering starts after all isolated atoms of all frames, then every
+        component (single atoms included) in atom order, frame by frame."""
+        return nframes * self.n_isolated + frame_index * self.nmol + m
 
     def masses(self, atoms) -> np.ndarray:
         return np.array([SYM2MASS[self.symbols[a]] for a in atoms], dtype=np.float64)

@@ -108,7 +108,8 @@ int dynpy_wrap_f64(const double* x, double* out, int64_t n, double L, dynpy_stre
 /* pdist_ortho (distances.py:155-242) for one frame, bit-exact: candidates visited in
  * (aa,bb,cc) order, strict '<' from dmax^2, no FMA contraction, compacted in row-major
  * upper-triangle order.  ux/uy/uz are read with element stride `stride`.
- * Outputs have capacity n(n-1)/2; *count (device int64) receives the number of rows.
+ * Outputs have capacity n(n-1)/2 — or pass all seven as NULL for a count-only call and size
+ * them from *count (device int64), which receives the number of rows.
  * ws: at least dynpy_pdist_workspace_bytes(n). */
 int64_t dynpy_pdist_workspace_bytes(int64_t n);
 int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, int64_t stride,
@@ -116,6 +117,12 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
                           double dmax, double* dx, double* dy, double* dz, double* dr,
                           int64_t* atom0, int64_t* atom1, int64_t* projection, int64_t* count,
                           void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+
+/* 3x3x3 block of periodic images of one frame (neighbors._worker, neighbors.py:160-199):
+ * coords [n_atoms][3][n_frames] (raw) -> out[3][27*n_atoms]; super atom p*n_atoms + l is atom l
+ * shifted by (i, j, k)*a with image number p = 9(i+1) + 3(j+1) + (k+1), i, j, k in {-1, 0, 1}. */
+int dynpy_supercell_f64(const double* coords, int64_t n_atoms, int64_t n_frames, int64_t frame,
+                        double a, double* out, dynpy_stream_t stream);
 
 /* Static-topology check: the reference re-detects bonds (dr <= rcov0 + rcov1 + bond_extra among
  * pairs with dr < dmax, distances.py:244-257) and molecules in EVERY frame; the CUDA path

@@ -171,6 +171,60 @@ def _specdens_vectors():
     print("golden: specdens_vectors.npz", len(out), "arrays")
 
 
+def _neighbors_case(name="nn_water"):
+    """neighbors.periodic_nearest_neighbors_by_atom of the reference (the cluster extraction of --inputs,
+    neighbors.py:22-118) on 8 waters x 3 frames: trajectory 01 raw (molecules whole), 02 the same frames
+    wrapped into the box (molecules split across the boundary, bonded through periodic images).
+    plus one Na atom.  Sources: the ion's label (custom Na radius so that it stays unbonded), a water atom
+    with default radii, two labels, a symbol.  Outputs: ref/<traj>_<tag>_nearest.csv, _nn<k>.csv."""
+    import numpy as np
+    import torch
+    refshim.import_reference()
+    import neighbors, parseMD
+    case = os.path.join(GOLD, name)
+    shutil.rmtree(case, ignore_errors=True)
+    os.makedirs(os.path.join(case, "ref"))
+    box = synth.water_box(8, seed=2, drift=0.02)
+    raw = box.frames(40, 43)
+    # a monatomic solute (the usual analyte of --inputs): isolated atoms exercise the molecule numbering
+    L = box.celldm
+    g = np.stack(np.meshgrid(*(np.linspace(0, L, 25, endpoint=False),) * 3, indexing="ij"), -1).reshape(-1, 3)
+    at = raw.permute(2, 0, 1).reshape(-1, 3).numpy()                       # all atoms of all frames
+    d = g[:, None, :] - at[None, :, :]
+    d -= L * np.round(d / L)
+    hole = g[np.argmax(np.sqrt((d ** 2).sum(-1)).min(1))]                   # the emptiest grid point
+    ion = torch.tensor(hole, dtype=torch.float64)[None, :, None] \
+        + 0.05 * torch.sin(torch.arange(3, dtype=torch.float64) + 1.0)[None, None, :]
+    raw = torch.cat([raw, ion.expand(1, 3, 3)], 0)
+    symbols = box.symbols + ["Na"]
+    for tr, arr in (("01", raw), ("02", torch.remainder(raw, box.celldm))):
+        os.makedirs(os.path.join(case, tr))
+        synth.write_xyz(os.path.join(case, tr, "traj.xyz"), arr, symbols)
+    body = PD_TMPL.format(trajs=["01", "02"], nat=len(symbols), start=1, end=3, mdp=4, samp=1, celldm=box.celldm,
+                          dt=0.002)
+    synth.write_params(os.path.join(case, "params.py"), body)
+    cwd = os.getcwd()
+    os.chdir(case)
+    try:
+        sys.path.insert(0, case)
+        import importlib
+        params = importlib.import_module("params")
+        PD = params.ParseDynamics
+        for tr in PD.trajs:
+            u, _ = parseMD.PARSE_MD(PD, PD.traj_dir + tr + "/")
+            for tag, source, sizes, kw in (("ion", [24], [0, 2, 4], dict(Na=0.1)), ("lab0", [0], [2], {}),
+                                           ("lab0_4", [0, 4], [3], dict(Na=0.1)), ("symO", "O", [1], dict(Na=0.1))):
+                dct = neighbors.periodic_nearest_neighbors_by_atom(u, source, PD.celldm, sizes, dmax=PD.celldm / 2, **kw)
+                dct["nearest"].to_csv(os.path.join("ref", "%s_%s_nearest.csv" % (tr, tag)), index=False)
+                for nn in sizes:
+                    dct[nn].atom.to_csv(os.path.join("ref", "%s_%s_nn%d.csv" % (tr, tag, nn)), index=False,
+                                        float_format="%.17g")
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(case)
+    print("golden:", name)
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -178,8 +232,11 @@ def main():
         return _leaf_vectors()
     if "--specdens-only" in sys.argv:
         return _specdens_vectors()
+    if "--neighbors-only" in sys.argv:
+        return _neighbors_case()
     _leaf_vectors()
     _specdens_vectors()
+    _neighbors_case()
     # the reference's own (only) known-answer set
     ref_nb = os.path.join(refshim.REFERENCE, "notebooks")
     dst = os.path.join(GOLD, "reference_iodide")

@@ -260,3 +260,54 @@ def test_cli_missing_key_and_bad_flag(tmp_path):
     assert r.returncode == 2 and "USAGE:" in r.stdout
     r = subprocess.run([sys.executable, "-m", "dynpy"], cwd=work, text=True, capture_output=True, env=env)
     assert r.returncode == 2 and "USAGE:" in r.stdout
+
+
+# ------------------------------------------------------------------ nearest-molecule clusters
+NN_CASES = [("ion", [24], [0, 2, 4], dict(Na=0.1)), ("lab0", [0], [2], {}), ("lab0_4", [0, 4], [3], dict(Na=0.1)),
+            ("symO", "O", [1], dict(Na=0.1))]
+
+
+@pytest.mark.parametrize("traj", ["01", "02"])
+def test_neighbors_vs_reference(ops, traj):
+    """dynpy_b200.neighbors.periodic_nearest_neighbors_by_atom against the tables the reference wrote:
+    every column of `nearest` (frame, idx, two, atom, molecule) and the cluster atoms (symbol, frame exact,
+    coordinates bit-exact) — raw (01) and wrapped (02: molecules bonded across periodic images) frames."""
+    from dynpy_b200 import neighbors, parseMD
+    PD = load_params("nn_water").ParseDynamics
+    PD.traj_dir = os.path.join(GOLDEN, "nn_water") + os.sep
+    tr = parseMD.PARSE_MD(PD, traj)
+    ref = os.path.join(GOLDEN, "nn_water", "ref")
+    for tag, source, sizes, kw in NN_CASES:
+        dct = neighbors.periodic_nearest_neighbors_by_atom(tr, source, PD.celldm, sizes, dmax=PD.celldm / 2, **kw)
+        hdr, rows = _csv(os.path.join(ref, "%s_%s_nearest.csv" % (traj, tag)))
+        assert list(dct["nearest"].columns) == hdr
+        want = np.array([[int(v) for v in r] for r in rows], dtype=np.int64).reshape(-1, 5)
+        np.testing.assert_array_equal(dct["nearest"].to_numpy(dtype=np.int64), want, err_msg="%s %s" % (traj, tag))
+        for nn in sizes:
+            hdr, rows = _csv(os.path.join(ref, "%s_%s_nn%d.csv" % (traj, tag, nn)))
+            atom = dct[nn].atom
+            assert list(atom.columns) == hdr
+            assert atom["symbol"].tolist() == [r[0] for r in rows]
+            assert atom["frame"].tolist() == [int(r[4]) for r in rows]
+            np.testing.assert_array_equal(atom[["x", "y", "z"]].to_numpy(), _num(rows, [1, 2, 3]))
+
+
+def test_neighbors_larger_box_vs_oracle(ops):
+    """32 waters + 1 ion (33*27 = 2673 atoms in the image block, 3.6e6 pairs -> the counted pdist path):
+    product vs the numpy restatement, wrapped coordinates."""
+    from dynpy_b200 import neighbors, parseMD, synth
+    box = synth.water_box(32, seed=9, drift=0.05)
+    raw = box.frames(100, 102)
+    L = box.celldm
+    ion = torch.tensor([[0.013 * L, 0.5 * L, 0.48 * L]], dtype=torch.float64)[:, :, None].expand(1, 3, 2)
+    raw = torch.remainder(torch.cat([raw, ion], 0), L)
+    symbols = box.symbols + ["Na"]
+    tr = parseMD.Trajectory(pos=raw.cuda().contiguous(), symbols=symbols, frames=np.array([5, 10], dtype=np.int64))
+    dct = neighbors.periodic_nearest_neighbors_by_atom(tr, [96], L, [6], dmax=L / 2, Na=0.1)
+    near, clusters = orc.nearest_neighbors(raw.numpy().transpose(2, 0, 1), symbols, [5, 10], [96], L, [6], dmax=L / 2,
+                                           Na=0.1)
+    np.testing.assert_array_equal(dct["nearest"].to_numpy(dtype=np.int64), near)
+    atom = dct[6].atom
+    assert atom["symbol"].tolist() == [c[0] for c in clusters[6]]
+    np.testing.assert_array_equal(atom[["x", "y", "z"]].to_numpy(), np.array([c[1:4] for c in clusters[6]]))
+    assert len(atom) >= 2 * (6 * 3 + 1)

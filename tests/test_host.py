@@ -178,10 +178,14 @@ def test_topology_numbering_and_pair_selection_match_oracle():
     assert topo.classify_exact("H(2)O(1)").all()
     with pytest.raises(KeyError):
         topo.classify_exact("H(4)C(1)")
-    # isolated atoms are numbered first (universe.py:426-431)
+    # isolated atoms: numbered first, then overwritten by the connected_components walk (universe.py:426-437),
+    # so all components are numbered in atom order starting at n_isolated (pinned by tests/golden/nn_water)
     t2 = topology.Topology(5, np.array([1]), np.array([3]), ["Na", "O", "Cl", "H", "K"])
-    np.testing.assert_array_equal(t2.mol_rank, [0, 3, 1, 3, 2])
-    assert t2.molecule_id(1, 3, 10) == 10 * 3 + 1 * 1 + 0
+    np.testing.assert_array_equal(t2.mol_rank, [0, 1, 2, 1, 3])
+    assert t2.n_isolated == 3 and t2.nmol == 4
+    np.testing.assert_array_equal(t2.frame_molecule_id(t2.mol_rank), [3, 4, 5, 4, 6])
+    assert t2.molecule_id(1, 1, 10) == 10 * 3 + 1 * 4 + 1
+    np.testing.assert_array_equal(orc._components(5, np.array([1]), np.array([3])), [3, 4, 5, 4, 6])
     for ptype, alabel in (("all", None), ("intra", None), ("inter", None), ("all", 1), ("all", 0)):
         pi, pj = DDparse.select_pairs(box.symbols, topo, 3, ptype, alabel)
         sym = np.array(box.symbols)

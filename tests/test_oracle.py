@@ -218,3 +218,40 @@ def test_finite_freq_formula_as_written():
                                [3.0 + 2e-4 * 5e3, 3.0 + 2e-4 * np.sqrt(5e7), 2.0 + 1e-4 * 5e3, 1.0 + 5e-5 * np.sqrt(5e7)],
                                rtol=1e-12)
     assert r["R"] > 0 and r["zf"] > 0
+
+
+# ---------------------------------------------------------------- nearest-molecule clusters
+NN_CASES = [("ion", [24], [0, 2, 4], dict(Na=0.1)), ("lab0", [0], [2], {}), ("lab0_4", [0, 4], [3], dict(Na=0.1)),
+            ("symO", "O", [1], dict(Na=0.1))]
+
+
+def nn_reference(traj, tag, sizes):
+    ref = os.path.join(GOLDEN, "nn_water", "ref")
+    _, near = _csv(os.path.join(ref, "%s_%s_nearest.csv" % (traj, tag)))
+    near = np.array([[int(v) for v in r] for r in near], dtype=np.int64).reshape(-1, 5)
+    clusters = {}
+    for nn in sizes:
+        _, rows = _csv(os.path.join(ref, "%s_%s_nn%d.csv" % (traj, tag, nn)))
+        clusters[nn] = [(r[0], float(r[1]), float(r[2]), float(r[3]), int(r[4])) for r in rows]
+    return near, clusters
+
+
+@pytest.mark.parametrize("traj", ["01", "02"])
+def test_nearest_neighbors_vs_reference(traj):
+    PD = load_params("nn_water").ParseDynamics
+    pos, sym, frames = orc.read_xyz(os.path.join(GOLDEN, "nn_water", traj, "traj.xyz"), PD.nat, PD.start_prod,
+                                    PD.end_prod, PD.sample_freq, PD.md_print_freq)
+    for tag, source, sizes, kw in NN_CASES:
+        near, clusters = orc.nearest_neighbors(pos, sym, frames, source, PD.celldm, sizes, dmax=PD.celldm / 2, **kw)
+        rnear, rclusters = nn_reference(traj, tag, sizes)
+        np.testing.assert_array_equal(near, rnear, err_msg="%s %s nearest" % (traj, tag))
+        for nn in sizes:
+            assert [c[0] for c in clusters[nn]] == [c[0] for c in rclusters[nn]]
+            assert [c[4] for c in clusters[nn]] == [c[4] for c in rclusters[nn]]
+            got = np.array([c[1:4] for c in clusters[nn]])
+            want = np.array([c[1:4] for c in rclusters[nn]])
+            np.testing.assert_array_equal(got, want, err_msg="%s %s nn%d coordinates" % (traj, tag, nn))
+    if traj == "02":   # the wrapped trajectory must exercise molecules bonded across periodic images
+        _, clusters = orc.nearest_neighbors(pos, sym, frames, [24], PD.celldm, [4], dmax=PD.celldm / 2, Na=0.1)
+        xyz = np.array([c[1:4] for c in clusters[4]])
+        assert (xyz < 0).any() or (xyz >= PD.celldm).any()
