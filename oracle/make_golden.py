@@ -65,6 +65,30 @@ def _traj_case(name, box, nprinted, start, end, samp, mdp, dt, extra_cls, flag, 
     print("golden:", name)
 
 
+class _WithSpectator:
+    """A synthetic box plus one unbonded atom at the emptiest grid point (monatomic species exercise the
+    molecule numbering of compute_molecule, universe.py:426-437)."""
+
+    def __init__(self, box, symbol, nprobe):
+        import numpy as np
+        import torch
+        self.box, self.celldm = box, box.celldm
+        self.symbols = box.symbols + [symbol]
+        self.nat = box.nat + 1
+        L = box.celldm
+        g = np.stack(np.meshgrid(*(np.linspace(0, L, 16, endpoint=False),) * 3, indexing="ij"), -1).reshape(-1, 3)
+        at = box.frames(0, nprobe).permute(2, 0, 1).reshape(-1, 3).numpy()
+        d = g[:, None, :] - at[None, :, :]
+        d -= L * np.round(d / L)
+        self.hole = torch.tensor(g[np.argmax(np.sqrt((d ** 2).sum(-1)).min(1))], dtype=torch.float64)
+
+    def frames(self, f0, f1):
+        import torch
+        t = torch.arange(f0, f1, dtype=torch.float64)
+        extra = self.hole[None, :, None] + 0.05 * torch.sin(0.3 * t)[None, None, :]
+        return torch.cat([self.box.frames(f0, f1), extra.expand(1, 3, f1 - f0)], 0)
+
+
 def _qr_case(name, nnuc, nframes, ntraj, seed, analyte="127I", symbol="I", with_traj0=False):
     case = os.path.join(GOLD, name)
     shutil.rmtree(case, ignore_errors=True)
@@ -234,6 +258,12 @@ def main():
         return _specdens_vectors()
     if "--neighbors-only" in sys.argv:
         return _neighbors_case()
+    if "--sr-ar-only" in sys.argv:
+        sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
+                  "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]
+        sr = "class SpinRotation:\n    mol_type = %r\n    nmol = %d\n    C_SR = %r\n"
+        return _traj_case("sr_methane_ar", _WithSpectator(synth.methane_box(4, seed=13), "Ar", 24), 24, 1, 24, 1, 1,
+                          0.001, sr % ("methane", 4, [16.495, 16.495, -1.875]), "-s", sr_out)
     _leaf_vectors()
     _specdens_vectors()
     _neighbors_case()
@@ -263,6 +293,8 @@ def main():
     m6 = synth.methane_box(6, seed=3)
     sr = "class SpinRotation:\n    mol_type = %r\n    nmol = %d\n    C_SR = %r\n"
     _traj_case("sr_methane", m6, 36, 2, 35, 1, 2, 0.001, sr % ("methane", 5, [16.495, 16.495, -1.875]), "-s", sr_out)
+    _traj_case("sr_methane_ar", _WithSpectator(synth.methane_box(4, seed=13), "Ar", 24), 24, 1, 24, 1, 1, 0.001,
+               sr % ("methane", 4, [16.495, 16.495, -1.875]), "-s", sr_out)
     _traj_case("sr_water", w8, 30, 1, 29, 2, 1, 0.001, sr % ("water", 8, [36.9, 33.5, 35.5]), "-s", sr_out)
 
 

@@ -107,7 +107,7 @@ def test_dd_pipeline_vs_reference(case, trajs):
 
 
 # ---------------------------------------------------------------- SR end to end
-@pytest.mark.parametrize("case", ["sr_methane", "sr_water"])
+@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar"])
 def test_sr_pipeline_vs_reference(case):
     P = load_params(case)
     PD, SR = P.ParseDynamics, P.SpinRotation
