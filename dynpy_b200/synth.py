@@ -35,9 +35,21 @@ _METHANE_BODY = np.array([[0.0, 0.0, 0.0],
                           [-_t, -_t, _t]])
 _METHANE_SYM = ["C", "H", "H", "H", "H"]
 
+# CH3-C#N along z, nitrile carbon first (so that the methyl rows (R, C) = (0, 1) and (C, H1) = (1, 2) exist in
+# the i < j pair table): C-C 1.458, C#N 1.157, C-H 1.09 Angstrom, H-C-C 109.5 degrees
+_hz, _hr = 1.458 + 1.09 * math.cos(math.radians(70.5)), 1.09 * math.sin(math.radians(70.5))
+_ACN_BODY = np.array([[0.0, 0.0, 0.0],
+                      [0.0, 0.0, 1.458],
+                      [_hr, 0.0, _hz],
+                      [-0.5 * _hr, 0.5 * math.sqrt(3.0) * _hr, _hz],
+                      [-0.5 * _hr, -0.5 * math.sqrt(3.0) * _hr, _hz],
+                      [0.0, 0.0, -1.157]])
+_ACN_SYM = ["C", "C", "H", "H", "H", "N"]
+
 SPECIES = {
     "water": (_WATER_BODY, _WATER_SYM),
     "methane": (_METHANE_BODY, _METHANE_SYM),
+    "acetonitrile": (_ACN_BODY, _ACN_SYM),
 }
 
 
@@ -145,6 +157,13 @@ def water_box(nmol, seed=2, **kw) -> RigidBox:
 def methane_box(nmol, seed=3, **kw) -> RigidBox:
     kw.setdefault("trans_amp", 1.0)
     return RigidBox("methane", nmol, methane_celldm(nmol), seed, **kw)
+
+
+def acetonitrile_box(nmol, seed=4, spacing=11.0, **kw) -> RigidBox:
+    """Dilute box (lattice spacing in bohr) so that no intermolecular contact comes near a bond cut-off."""
+    ncell = int(math.ceil(nmol ** (1.0 / 3.0) - 1e-9))
+    kw.setdefault("trans_amp", 0.3)
+    return RigidBox("acetonitrile", nmol, spacing * ncell, seed, **kw)
 
 
 def efg_series(nnuc: int, nframes: int, seed: int = 1, device="cpu", nmodes: int = 6,

@@ -249,6 +249,15 @@ def _neighbors_case(name="nn_water"):
     print("golden:", name)
 
 
+# acetonitrile through the 'methyl' (top: the five methyl_indeces atoms only / global_momentum: whole molecule)
+# and 'ring' axis rules (SRrax.py:405-432, SRparse.py:155-163)
+_SR_ACN = ("class SpinRotation:\n    mol_type = %r\n    identifier = 'H(3)C(2)N(1)'\n    nmol = 4\n"
+           "    C_SR = [1.0, 1.0, 12.0]\n    methyl_indeces = %r\n    global_momentum = %r\n")
+_SR_METHYL_CASES = [("sr_methyl", _SR_ACN % ("methyl", [0, 1, 2, 3, 4], False)),
+                    ("sr_methyl_global", _SR_ACN % ("methyl", [0, 1, 2, 3, 4], True)),
+                    ("sr_ring", _SR_ACN % ("ring", [0, 2], False))]
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -258,6 +267,12 @@ def main():
         return _specdens_vectors()
     if "--neighbors-only" in sys.argv:
         return _neighbors_case()
+    if "--sr-methyl-only" in sys.argv:
+        sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
+                  "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]
+        for name, cls in _SR_METHYL_CASES:
+            _traj_case(name, synth.acetonitrile_box(4, seed=4), 22, 1, 22, 1, 1, 0.001, cls, "-s", sr_out)
+        return
     if "--sr-ar-only" in sys.argv:
         sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
                   "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]
@@ -295,6 +310,8 @@ def main():
     _traj_case("sr_methane", m6, 36, 2, 35, 1, 2, 0.001, sr % ("methane", 5, [16.495, 16.495, -1.875]), "-s", sr_out)
     _traj_case("sr_methane_ar", _WithSpectator(synth.methane_box(4, seed=13), "Ar", 24), 24, 1, 24, 1, 1, 0.001,
                sr % ("methane", 4, [16.495, 16.495, -1.875]), "-s", sr_out)
+    for name, cls in _SR_METHYL_CASES:
+        _traj_case(name, synth.acetonitrile_box(4, seed=4), 22, 1, 22, 1, 1, 0.001, cls, "-s", sr_out)
     _traj_case("sr_water", w8, 30, 1, 29, 2, 1, 0.001, sr % ("water", 8, [36.9, 33.5, 35.5]), "-s", sr_out)
 
 

@@ -187,7 +187,7 @@ def test_topology_change_is_detected(ops):
 
 
 # ------------------------------------------------------------------ SR
-@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar"])
+@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring"])
 def test_cli_srrelax_vs_reference_csv(tmp_path, case, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-s", work)

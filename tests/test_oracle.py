@@ -107,13 +107,15 @@ def test_dd_pipeline_vs_reference(case, trajs):
 
 
 # ---------------------------------------------------------------- SR end to end
-@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar"])
+@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring"])
 def test_sr_pipeline_vs_reference(case):
     P = load_params(case)
     PD, SR = P.ParseDynamics, P.SpinRotation
     pos, sym, frames = orc.read_xyz(os.path.join(GOLDEN, case, "01", "traj.xyz"), PD.nat, PD.start_prod,
                                     PD.end_prod, PD.sample_freq, PD.md_print_freq)
-    out = orc.sr_pipeline(pos, sym, frames, PD.celldm, PD.timestep, SR.mol_type, SR.nmol, SR.C_SR)
+    out = orc.sr_pipeline(pos, sym, frames, PD.celldm, PD.timestep, SR.mol_type, SR.nmol, SR.C_SR,
+                          identifier=getattr(SR, "identifier", None), methyl_indeces=getattr(SR, "methyl_indeces", None),
+                          global_momentum=getattr(SR, "global_momentum", False))
     ref = os.path.join(GOLDEN, case, "ref")
     hdr, rows = _csv(os.path.join(ref, "01__J_cart.csv"))
     a = np.array([[float(x) for x in r[1:]] for r in rows])
