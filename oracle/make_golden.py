@@ -258,6 +258,15 @@ _SR_METHYL_CASES = [("sr_methyl", _SR_ACN % ("methyl", [0, 1, 2, 3, 4], False)),
                     ("sr_ring", _SR_ACN % ("ring", [0, 2], False))]
 
 
+def _dd_hetero_case():
+    """13C-1H dipolar relaxation of the methyl carbon of acetonitrile: analyte_label = 1 (mol-atom index of the
+    methyl C), unlike-spin rate formula (ddrax.py:270-271), intramolecular pairs only."""
+    dd_het = ("class Dipolar:\n    identifier = 'H(3)C(2)N(1)'\n    pair_type = 'intra'\n    rmax = 8.0\n"
+              "    analyte_label = 1\n    analyte_species = '13C'\n")
+    _traj_case("dd_hetero_13C", synth.acetonitrile_box(4, seed=4), 40, 1, 40, 1, 2, 0.002, dd_het, "-d",
+               ["{traj}/avg-acf.csv", "DD-results.csv"])
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -273,6 +282,8 @@ def main():
         for name, cls in _SR_METHYL_CASES:
             _traj_case(name, synth.acetonitrile_box(4, seed=4), 22, 1, 22, 1, 1, 0.001, cls, "-s", sr_out)
         return
+    if "--dd-hetero-only" in sys.argv:
+        return _dd_hetero_case()
     if "--sr-ar-only" in sys.argv:
         sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
                   "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]
@@ -302,6 +313,8 @@ def main():
     dd_het = ("class Dipolar:\n    identifier = 'H(2)O(1)'\n    pair_type = 'all'\n    rmax = 16.0\n"
               "    analyte_label = 1\n    analyte_species = '1H'\n")
     _traj_case("dd_analyte_label", w8, 30, 1, 30, 1, 1, 0.002, dd_het, "-d", dd_out)
+
+    _dd_hetero_case()
 
     sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
               "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]

@@ -99,7 +99,8 @@ def test_qr_golden_iodide_rates_on_gpu(ops):
 
 # ------------------------------------------------------------------ DD
 @pytest.mark.parametrize("case,trajs", [("dd_gapless_all", ["01"]), ("dd_gaps_inter", ["01"]),
-                                         ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"])])
+                                         ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"]),
+                                         ("dd_hetero_13C", ["01"])])
 def test_cli_ddrelax_vs_reference_csv(tmp_path, case, trajs, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-d", work)

@@ -90,7 +90,8 @@ def _run_dd(case, traj="01"):
 
 
 @pytest.mark.parametrize("case,trajs", [("dd_gapless_all", ["01"]), ("dd_gaps_inter", ["01"]),
-                                         ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"])])
+                                         ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"]),
+                                         ("dd_hetero_13C", ["01"])])
 def test_dd_pipeline_vs_reference(case, trajs):
     _, res = _csv(os.path.join(GOLDEN, case, "ref", "DD-results.csv"))
     for k, traj in enumerate(trajs):
@@ -101,7 +102,10 @@ def test_dd_pipeline_vs_reference(case, trajs):
         np.testing.assert_allclose(out["time"], a[:, 1], rtol=1e-14)
         for c in range(7):
             ref = a[:, 2 + c]
-            assert np.max(np.abs(out["G"][c] - ref)) <= 1e-11 * np.max(np.abs(ref))
+            # G_r of rigid intramolecular pairs is rounding noise (r^-3 - mean = 0): judged on the scale of the
+            # r^-3-weighted columns
+            scale = np.max(np.abs(a[:, 6:9])) if c == 3 else np.max(np.abs(ref))
+            assert np.max(np.abs(out["G"][c] - ref)) <= 1e-11 * scale
         want = [float(x) for x in res[k][1:4]]
         np.testing.assert_allclose([out["rate"], out["tau_c"], out["F0"]], want, rtol=1e-10)
 
