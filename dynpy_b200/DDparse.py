@@ -14,9 +14,8 @@ from .config import default_simpson_mode
 from .helper import which_trajs
 
 
-def select_pairs(symbols, topo, nat_per_mol, pair_type, analyte_label):
-    """Pair rows the reference keeps (DDparse.py:53-60): H–H (or analyte_label–H) with
-    label0 < label1, intra / inter / all by molecule membership.  Returns int32 arrays."""
+def _eligible(symbols, nat_per_mol, analyte_label):
+    """(i, j, sel): all label pairs i < j and the symbol / analyte filter of DDparse.py:53-56."""
     A = len(symbols)
     sym = np.array(symbols)
     i, j = np.triu_indices(A, k=1)
@@ -25,12 +24,44 @@ def select_pairs(symbols, topo, nat_per_mol, pair_type, analyte_label):
         sel = (mai[i] == analyte_label) & (sym[j] == 'H')
     else:
         sel = (sym[i] == 'H') & (sym[j] == 'H')
+    return i, j, sel
+
+
+def select_pairs(symbols, topo, nat_per_mol, pair_type, analyte_label):
+    """Pair rows the reference keeps (DDparse.py:53-60): H–H (or analyte_label–H) with
+    label0 < label1, intra / inter / all by molecule membership.  Returns int32 arrays."""
+    i, j, sel = _eligible(symbols, nat_per_mol, analyte_label)
     m = topo.mol_rank
     if pair_type == 'intra':
         sel &= m[i] == m[j]
     elif pair_type == 'inter':
         sel &= m[i] != m[j]
     return i[sel].astype(np.int32), j[sel].astype(np.int32)
+
+
+def select_pairs_dynamic(symbols, ft, nat_per_mol, pair_type, analyte_label):
+    """The same for a trajectory whose bond list is not the same in every frame (ft: FrameTopologies).  The
+    reference filters pair ROWS by the molecule ids of their own frame, so a pair can be intramolecular in some
+    frames and intermolecular in others.  Returns (pi, pj) for the pairs whose status never changes and
+    (mi, mj, mask [K, F] uint8) for those that do, mask = frames in which the row is kept."""
+    i, j, sel = _eligible(symbols, nat_per_mol, analyte_label)
+    base_same = ft.base.mol_rank[i] == ft.base.mol_rank[j]
+    if pair_type not in ('intra', 'inter') or not ft.frames:
+        pi, pj = select_pairs(symbols, ft.base, nat_per_mol, pair_type, analyte_label)
+        return pi, pj, None
+    want_same = pair_type == 'intra'
+    changed = np.zeros(len(i), dtype=bool)
+    same_f = {}
+    for f, t in ft.frames.items():
+        same_f[f] = t.mol_rank[i] == t.mol_rank[j]
+        changed |= same_f[f] != base_same
+    changed &= sel
+    static = sel & (base_same == want_same) & ~changed
+    mask = np.repeat((base_same[changed] == want_same)[:, None], ft.nframes, axis=1)
+    for f, sf in same_f.items():
+        mask[:, f] = sf[changed] == want_same
+    return (i[static].astype(np.int32), j[static].astype(np.int32),
+            (i[changed].astype(np.int32), j[changed].astype(np.int32), mask.astype(np.uint8)))
 
 
 def dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson_mode):
@@ -41,13 +72,15 @@ def dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson
         dmax = 15
     cell = (float(PD.celldm),) * 3
     wrapped = ops.wrap(tr.pos, cell[0])
-    topo, _ = topology.build_topology(wrapped, tr.symbols, cell, dmax, bond_extra=0.45)
-    topo.classify_exact(DD.identifier)  # raises like Molecule.classify when the formula is absent
+    ft, _ = topology.build_topology(wrapped, tr.symbols, cell, dmax, bond_extra=0.45, dynamic=True)
+    ft.base.classify_exact(DD.identifier)  # raises like Molecule.classify when the formula is absent
     nat_per_mol = topology.atoms_per_formula(DD.identifier)
-    pi, pj = select_pairs(tr.symbols, topo, nat_per_mol, pair_type, analyte_label)
+    pi, pj, changing = select_pairs_dynamic(tr.symbols, ft, nat_per_mol, pair_type, analyte_label)
     dev = wrapped.device
+    if changing is not None:
+        changing = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in changing)
     G, hit, n_spins, info = ddrax.pair_acf_sum(wrapped, torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev),
-                                               cell, dmax)
+                                               cell, dmax, masked=changing)
     if n_spins == 0:
         raise ValueError("no pair of the requested kind is ever inside rmax=%r" % (dmax,))
     G = (G[:, hit] * (2.0 / n_spins)).contiguous()

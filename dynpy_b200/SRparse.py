@@ -28,9 +28,11 @@ def frame_step(frames: np.ndarray, nat: int):
     return uniq[-1]
 
 
-def select_molecules(topo, SR):
-    """Molecules the reference keeps (SRparse.py:142-176): exact formula match, labelled by the rank
-    of their atom-label tuple, label < nmol.  Returns list of (molecule_label, mol_rank, atoms)."""
+def select_molecules(ft, SR):
+    """Molecules the reference keeps (SRparse.py:142-176): exact formula match in a frame, labelled by the rank of
+    their atom-label tuple among all such tuples of all frames, present (as exactly that connected component)
+    in EVERY frame, label < nmol.  `ft`: topology.FrameTopologies.  Returns list of (molecule_label, mol_rank in
+    the indexing frame, atoms) in molecule order."""
     mol_type = SR.mol_type
     if mol_type in _FORMULA:
         ident = _FORMULA[mol_type]
@@ -38,11 +40,21 @@ def select_molecules(topo, SR):
         ident = SR.identifier
     else:
         sys.exit("Only molecule types methane, water, acetonitrile, and methyl are supported")
+    topo = ft.base
     hit = topo.classify_exact(ident)
-    tuples = sorted(topo.groups[m] for m in range(topo.nmol) if hit[m])
-    label_of = {t: k for k, t in enumerate(tuples)}
-    keep = [(label_of[topo.groups[m]], m, topo.groups[m]) for m in range(topo.nmol) if hit[m]]
-    keep = [k for k in keep if k[0] < SR.nmol]
+    base = {topo.groups[m]: m for m in range(topo.nmol) if hit[m]}
+    every = set(base)
+    tuples = set(base)
+    for t in ft.frames.values():
+        try:
+            h = t.classify_exact(ident)
+        except KeyError:
+            h = np.zeros(t.nmol, dtype=bool)
+        here = {t.groups[m] for m in range(t.nmol) if h[m]}
+        tuples |= here
+        every &= here
+    label_of = {t: k for k, t in enumerate(sorted(tuples))}
+    keep = [(label_of[t], base[t], t) for t in every if label_of[t] < SR.nmol]
     keep.sort(key=lambda k: k[1])  # groupby('molecule') order: by molecule id inside the frame
     return keep, topology.atoms_per_formula(ident)
 
@@ -93,8 +105,9 @@ def sr_trajectory(tr, PD, SR, simpson_mode, per_molecule_acfs=True):
         first = 0
     F = len(frames)
     wrapped = ops.wrap(tr.pos[:, :, first:].contiguous(), cell[0])
-    topo, two0 = topology.build_topology(wrapped, tr.symbols, cell, 8.0, bond_extra=0.45)
-    keep, nat_per_mol = select_molecules(topo, SR)
+    ft, two0 = topology.build_topology(wrapped, tr.symbols, cell, 8.0, bond_extra=0.45, dynamic=True)
+    topo = ft.base
+    keep, nat_per_mol = select_molecules(ft, SR)
     if not keep:
         raise ValueError("no molecule of type %r found" % SR.mol_type)
     nmol = len(keep)
@@ -121,7 +134,7 @@ def sr_trajectory(tr, PD, SR, simpson_mode, per_molecule_acfs=True):
     tdev = torch.from_numpy(frames).to(dev).to(torch.float64) * float(PD.timestep)
     tx, ty, tz, r = compute_SR_rax(tdev, acf_mean, SR, simpson_mode)
     out = dict(frames=frames, keep=keep, J=J, omega=om, axes=ax, acf_mean=acf_mean, time=tdev, tau=(tx, ty, tz), rate=r,
-               topo=topo, nframes_total=F)
+               topo=topo, frame_topologies=ft, nframes_total=F)
     if per_molecule_acfs:
         out["acf_each"] = ops.wk_acf_each(J.reshape(nmol * 3, F).contiguous(), M=M).reshape(nmol, 3, F)
     return out
@@ -131,8 +144,7 @@ def _tables(out):
     """Host DataFrames with the reference's row order and columns."""
     frames, keep = out["frames"], out["keep"]
     F, nmol = len(frames), len(keep)
-    topo = out["topo"]
-    mol_ids = np.array([[topo.molecule_id(f, m, F) for (_, m, _) in keep] for f in range(F)])  # [F, nmol]
+    mol_ids = out["frame_topologies"].molecule_ids([atoms[0] for (_, _, atoms) in keep])  # [F, nmol]
     labels = np.array([lab for (lab, _, _) in keep])
     fr_col = np.repeat(frames, nmol)
     mol_col = mol_ids.reshape(-1)

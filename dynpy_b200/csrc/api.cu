@@ -417,7 +417,26 @@ int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_fr
     const unsigned long long init[2] = {0ull, ~0ull};
     DYNPY_CHECK(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st), "topology init");
     DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
-                                      (unsigned long long*)out, st), "topology check");
+                                      (unsigned long long*)out, nullptr, 0, st), "topology check");
+    return DYNPY_OK;
+}
+
+int dynpy_topology_events_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const double* rcov,
+                              double bond_extra, const uint8_t* expect, double a, double b, double c, double dmax,
+                              int64_t* events, int64_t capacity, uint64_t* out, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!coords || !rcov || !expect || !out || !events || capacity < 1 || n_atoms < 1 || n_frames < 1 ||
+        n_atoms > 65535) {
+        set_error("dynpy_topology_events_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    const unsigned long long init[3] = {0ull, ~0ull, 0ull};
+    DYNPY_CHECK(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st), "topology init");
+    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
+                                      (unsigned long long*)out, (i64*)events, capacity, st), "topology events");
     return DYNPY_OK;
 }
 
@@ -519,6 +538,15 @@ int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int6
                                      const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
                                      double rmax, double* G, int64_t M, void* ws, int64_t ws_bytes,
                                      dynpy_stream_t stream) {
+    return dynpy_dd_pairs_masked_to_acf_f64(coords, n_atoms, n_frames, pair_i, pair_j, n_pairs, a, b, c, rmax, nullptr,
+                                            G, nullptr, nullptr, M, ws, ws_bytes, stream);
+}
+
+int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                                     const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
+                                     double rmax, const uint8_t* mask, double* G, int64_t* pair_frames,
+                                     int32_t* frame_hit, int64_t M, void* ws, int64_t ws_bytes,
+                                     dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_M(M, n_frames);
     if (rc) return rc;
@@ -555,7 +583,9 @@ int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int6
     for (i64 p0 = 0; p0 < n_pairs; p0 += cap) {
         const i64 cnt = n_pairs - p0 < cap ? n_pairs - p0 : cap;
         DYNPY_CHECK(launch_dd_ragged_words(coords, N, pair_i, pair_j, p0, cnt, a, b, c, rmax, W, fidx, lens, scale,
-                                           bias, st), "dd ragged words");
+                                           bias, mask, st), "dd ragged words");
+        DYNPY_CHECK(launch_dd_ragged_presence(fidx, lens, N, cnt, pair_frames ? (i64*)pair_frames + p0 : nullptr,
+                                              frame_hit, st), "dd ragged presence");
         PlanarLoader ld;
         memset(&ld, 0, sizeof(ld));
         ld.re = W;

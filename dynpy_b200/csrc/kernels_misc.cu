@@ -256,7 +256,7 @@ cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const in
 __global__ void __launch_bounds__(256)
 k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
                  const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
-                 unsigned long long* __restrict__ out) {
+                 unsigned long long* __restrict__ out, i64* __restrict__ events, i64 cap) {
     const i64 n = (i64)blockIdx.x * 256 + threadIdx.x;
     const i64 i = blockIdx.y;
     if (n >= N) return;
@@ -270,7 +270,13 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
         axis_min(zi, __ldg(X + (j * 3 + 2) * N + n), c, d, sz);
         const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
         const bool bond = (r2 < dmax2) && (sqrt(r2) <= __dadd_rn(__dadd_rn(ri, rcov[j]), extra));
-        if (bond != (expect[i * A + j] != 0)) ++bad;
+        if (bond != (expect[i * A + j] != 0)) {
+            ++bad;
+            if (events) {  // (frame, i, j) of every bond flag that differs from the indexing frame's
+                const unsigned long long k = atomicAdd(out + 2, 1ull);
+                if ((i64)k < cap) { events[3 * k] = n; events[3 * k + 1] = i; events[3 * k + 2] = j; }
+            }
+        }
     }
     if (bad) {
         atomicAdd(out, bad);
@@ -279,10 +285,10 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
 }
 cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
-                                  unsigned long long* out, cudaStream_t st) {
+                                  unsigned long long* out, i64* events, i64 cap, cudaStream_t st) {
     if (A < 2 || N < 1) return cudaSuccess;
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)(A - 1));
-    k_topology_check<<<grid, 256, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax, out);
+    k_topology_check<<<grid, 256, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax, out, events, cap);
     return cudaGetLastError();
 }
 
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(256)
 k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
                   i64 pair0, double a, double b, double c, double rmax2, double* __restrict__ W,
                   int* __restrict__ fidx, i64* __restrict__ lens, double* __restrict__ scale,
-                  double* __restrict__ bias) {
+                  double* __restrict__ bias, const unsigned char* __restrict__ mask) {
     __shared__ int wcnt[8];
     __shared__ i64 base;
     __shared__ double sh[8];
@@ -318,7 +324,7 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
             axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, dy, sy);
             axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, dz, sz);
             const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
-            ok = r2 < rmax2;
+            ok = r2 < rmax2 && (!mask || mask[p * N + n]);  // mask: frames in which the pair row passes the molecule filter
             if (ok) d = dd_words(dx, dy, dz, r2);
         }
         const unsigned ball = __ballot_sync(0xffffffffu, ok);
@@ -355,10 +361,26 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
 }
 cudaError_t launch_dd_ragged_words(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 npairs,
                                    double a, double b, double c, double rmax, double* W, int* fidx, i64* lens,
-                                   double* scale, double* bias, cudaStream_t st) {
+                                   double* scale, double* bias, const unsigned char* mask, cudaStream_t st) {
     if (npairs <= 0) return cudaSuccess;
     k_dd_ragged_words<<<(unsigned)npairs, 256, 0, st>>>(X, N, pi, pj, pair0, a, b, c, rmax * rmax, W, fidx, lens,
-                                                        scale, bias);
+                                                        scale, bias, mask);
+    return cudaGetLastError();
+}
+
+// per pair of a ragged batch: number of frames it is present in, and the frames hit by any pair
+__global__ void k_dd_ragged_presence(const int* __restrict__ fidx, const i64* __restrict__ lens, i64 N,
+                                     i64* __restrict__ pair_frames, int* __restrict__ frame_hit) {
+    const i64 pl = blockIdx.x;
+    const i64 np = lens[pl * 7];
+    if (threadIdx.x == 0 && pair_frames) pair_frames[pl] = np;
+    if (frame_hit)
+        for (i64 k = threadIdx.x; k < np; k += blockDim.x) frame_hit[fidx[pl * N + k]] = 1;
+}
+cudaError_t launch_dd_ragged_presence(const int* fidx, const i64* lens, i64 N, i64 npairs, i64* pair_frames,
+                                      int* frame_hit, cudaStream_t st) {
+    if (npairs <= 0 || (!pair_frames && !frame_hit)) return cudaSuccess;
+    k_dd_ragged_presence<<<(unsigned)npairs, 256, 0, st>>>(fidx, lens, N, pair_frames, frame_hit);
     return cudaGetLastError();
 }
 

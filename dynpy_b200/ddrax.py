@@ -24,13 +24,15 @@ def gapless(cell, rmax) -> bool:
     return float(rmax) ** 2 > half_diag2 * (1.0 + 1e-9)
 
 
-def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True):
+def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True, masked=None):
     """Sum over pairs of the 7 per-pair ACFs with the reference's presence semantics.
 
     wrapped [A,3,F] wrapped coords (cuda), pair_i/pair_j int32 atom labels (i < j).
     Returns (G [7,F] float64 cuda — NOT yet scaled by 2/N_spins, hit [F] bool cuda,
     n_spins int, info dict).  With torch.distributed initialised and shard=True the pairs are
-    split over the ranks and the result is all-reduced (every rank returns the total)."""
+    split over the ranks and the result is all-reduced (every rank returns the total).
+    masked = (mi, mj, mask [K,F] uint8): extra pairs that pass the reference's molecule filter only in the frames
+    flagged by mask (pairs whose intra/inter status changes along the trajectory); handled by rank 0."""
     dev = wrapped.device
     A, _, F = wrapped.shape
     P = int(pair_i.numel())
@@ -65,6 +67,16 @@ def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True):
             ops.dd_pairs_ragged_to_acf(wrapped, part_i, part_j, cell, rmax, M=M, G=G)
             label_used[part_i.long()] = 1
             label_used[part_j.long()] = 1
+    if masked is not None and masked[0].numel() and (not shard or dist.rank_world()[0] == 0):
+        mi, mj, mk = masked
+        nfr = torch.zeros(mi.numel(), dtype=torch.int64, device=dev)
+        ops.dd_pairs_ragged_to_acf(wrapped, mi, mj, cell, rmax, M=M, G=G, mask=mk, pair_frames=nfr, frame_hit=hit)
+        seen = nfr > 0
+        label_used[mi[seen].long()] = 1
+        label_used[mj[seen].long()] = 1
+        info["partial"] += int(seen.sum())
+        info["absent"] += int((~seen).sum())
+        info["pairs"] += int(mi.numel())
     if shard:
         dist.allreduce_sum_(G)
         dist.allreduce_sum_(hit)

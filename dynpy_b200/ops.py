@@ -6,6 +6,7 @@ contiguous, float64 / int64 / int32 as documented; there is no CPU path.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -218,6 +219,29 @@ def topology_check(coords, rcov, bond_extra, expect, cell, dmax):
     return int(bad), (int(first) if bad else -1)
 
 
+def topology_events(coords, rcov, bond_extra, expect, cell, dmax, capacity=1 << 16):
+    """Pair-frames whose bond flag differs from `expect`: int64 array [k, 3] of (frame index, i, j), host.
+    Raises when more than `capacity` differ (a trajectory that reactive is outside the static-topology design)."""
+    lib = _lib.load()
+    coords = _chk(coords, torch.float64, "coords")
+    rcov = _chk(rcov, torch.float64, "rcov")
+    expect = _chk(expect, torch.uint8, "expect")
+    A, three, F = coords.shape
+    out = torch.zeros(3, dtype=torch.int64, device=coords.device)
+    ev = torch.empty((capacity, 3), dtype=torch.int64, device=coords.device)
+    with torch.cuda.device(coords.device):
+        rc = lib.dynpy_topology_events_f64(coords.data_ptr(), A, F, rcov.data_ptr(), float(bond_extra), expect.data_ptr(),
+                                           float(cell[0]), float(cell[1]), float(cell[2]), float(dmax), ev.data_ptr(),
+                                           int(capacity), out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_topology_events_f64")
+    bad, first, n = out.tolist()
+    if n > capacity:
+        raise _lib.DynpyError("bond topology differs from the indexing frame in %d pair-frames (> %d): too reactive for "
+                              "the static-topology indexing" % (n, capacity))
+    e = ev[:n].cpu().numpy()
+    return e[np.lexsort((e[:, 2], e[:, 1], e[:, 0]))] if n else e
+
+
 def dd_pair_count(coords, pair_i, pair_j, cell, rmax, frame_hit=None):
     """Frames in which each pair is inside rmax; optional int32 frame_hit[F] gets 1 where any pair is."""
     lib = _lib.load()
@@ -260,8 +284,11 @@ def dd_pairs_to_spectrum(coords, pair_i, pair_j, cell, M=None, spectrum=None, ws
     return spectrum
 
 
-def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 2 << 30):
-    """Ragged dipolar path: G[7, F] += per-pair ACFs binned at the k-th present frame."""
+def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 2 << 30, mask=None,
+                           pair_frames=None, frame_hit=None):
+    """Ragged dipolar path: G[7, F] += per-pair ACFs binned at the k-th present frame.  Optional mask [P, F]
+    uint8 (frames in which the pair row passes the molecule filter), pair_frames [P] int64 out (frames present),
+    frame_hit [F] int32 (set to 1 where some pair is present)."""
     lib = _lib.load()
     coords = _chk(coords, torch.float64, "coords")
     pair_i = _chk(pair_i, torch.int32, "pair_i")
@@ -272,6 +299,13 @@ def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, w
         G = torch.zeros((7, F), dtype=torch.float64, device=coords.device)
     _chk(G, torch.float64, "G")
     npairs = pair_i.numel()
+    if mask is not None:
+        mask = _chk(mask, torch.uint8, "mask")
+        assert mask.shape == (npairs, F)
+    if pair_frames is not None:
+        pair_frames = _chk(pair_frames, torch.int64, "pair_frames")
+    if frame_hit is not None:
+        frame_hit = _chk(frame_hit, torch.int32, "frame_hit")
     one = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 1))
     two = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 2))
     per = two - one
@@ -279,10 +313,13 @@ def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, w
     with torch.cuda.device(coords.device):
         wsb = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, n))
         ws = workspace(coords.device, wsb)
-        rc = lib.dynpy_dd_pairs_ragged_to_acf_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), npairs,
+        rc = lib.dynpy_dd_pairs_masked_to_acf_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), npairs,
                                                   float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
-                                                  G.data_ptr(), M, ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "dynpy_dd_pairs_ragged_to_acf_f64")
+                                                  mask.data_ptr() if mask is not None else None, G.data_ptr(),
+                                                  pair_frames.data_ptr() if pair_frames is not None else None,
+                                                  frame_hit.data_ptr() if frame_hit is not None else None,
+                                                  M, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dynpy_dd_pairs_masked_to_acf_f64")
     return G
 
 

@@ -129,9 +129,52 @@ class Topology:
         return np.array([SYM2MASS[self.symbols[a]] for a in atoms], dtype=np.float64)
 
 
+class FrameTopologies:
+    """The topology of the indexing frame plus the (few) frames whose bond list differs from it — what the
+    reference's per-frame compute_molecule sees (universe.py:411-451).
+
+    at(f)            Topology of frame index f
+    molecule_ids(..) the 'molecule' numbers of the reference's all-frames universe: numbering starts after the
+                     isolated atoms of ALL frames, then the components of frame 0, frame 1, ... in atom order
+    """
+
+    def __init__(self, base: Topology, changes: dict, nframes: int):
+        self.base = base
+        self.nframes = nframes
+        self.frames = {}
+        for f, pairs in changes.items():
+            bonds = set(base.bonds)
+            for ij in pairs:
+                bonds.symmetric_difference_update([ij])
+            b = sorted(bonds)
+            self.frames[f] = Topology(base.nat, np.array([x[0] for x in b], dtype=np.int64),
+                                      np.array([x[1] for x in b], dtype=np.int64), base.symbols)
+        ncomp = np.full(nframes, base.nmol, dtype=np.int64)
+        niso = np.full(nframes, base.n_isolated, dtype=np.int64)
+        for f, t in self.frames.items():
+            ncomp[f], niso[f] = t.nmol, t.n_isolated
+        self._start = int(niso.sum()) + np.concatenate([[0], np.cumsum(ncomp)[:-1]])
+
+    def at(self, f: int) -> Topology:
+        return self.frames.get(f, self.base)
+
+    def molecule_ids(self, first_atoms) -> np.ndarray:
+        """[F, len(first_atoms)]: id, in every frame, of the molecule that holds each of the given atoms."""
+        first_atoms = np.asarray(first_atoms, dtype=np.int64)
+        out = self._start[:, None] + self.base.mol_rank[first_atoms][None, :]
+        for f, t in self.frames.items():
+            out[f] = self._start[f] + t.mol_rank[first_atoms]
+        return out
+
+
 def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra: float = 0.45,
-                   check_frames=None) -> tuple[Topology, dict]:
-    """Topology from frame 0 (+ consistency check on `check_frames`, default middle and last)."""
+                   check_frames=None, dynamic: bool = False):
+    """Topology from frame 0, verified on every frame by the device scan.
+
+    dynamic=False: a bond list that changes along the trajectory raises (the dipolar path indexes pairs from a
+    static topology).  dynamic=True: returns (FrameTopologies, two0) instead — the deviating frames are listed by
+    the device scan and re-indexed on the host, so that molecules which are not intact in every frame can be
+    dropped the way the reference does (SRparse.py:171-176)."""
     A, _, F = wrapped.shape
     two0 = frame_pairs(wrapped, cell, 0, dmax)
     b0 = bonded(two0, symbols, bond_extra)
@@ -140,6 +183,12 @@ def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra
         expect = torch.zeros((A, A), dtype=torch.uint8)
         expect[torch.from_numpy(two0["i"][b0]), torch.from_numpy(two0["j"][b0])] = 1
         rc = torch.tensor([SYM2COVRAD[s] for s in symbols], dtype=torch.float64, device=wrapped.device)
+        if dynamic:
+            ev = ops.topology_events(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
+            changes = {}
+            for f, i, j in ev.tolist():
+                changes.setdefault(int(f), []).append((int(i), int(j)))
+            return FrameTopologies(topo, changes, F), two0
         bad, first = ops.topology_check(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
         if bad:
             raise RuntimeError("bond topology changes along the trajectory (%d pair-frames differ from frame index 0, "

@@ -132,6 +132,16 @@ int dynpy_supercell_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
 int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
                              const double* rcov, double bond_extra, const uint8_t* expect, double a,
                              double b, double c, double dmax, uint64_t* out, dynpy_stream_t stream);
+/* Same scan, additionally listing the differences: events[k] = (frame, i, j) for every pair-frame whose
+ * bond flag differs from `expect` (unordered; only the first `capacity` are stored), out[0] = mismatching
+ * pair-frames, out[1] = first such frame, out[2] = number of events found (may exceed capacity).
+ * Lets the host reproduce the reference's per-frame molecule detection (universe.py:411-451,
+ * SRparse.py:171-176: molecules that are not intact in every frame are dropped) from a static topology
+ * plus the few frames that deviate from it. */
+int dynpy_topology_events_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                              const double* rcov, double bond_extra, const uint8_t* expect, double a,
+                              double b, double c, double dmax, int64_t* events, int64_t capacity,
+                              uint64_t* out, dynpy_stream_t stream);
 
 /* frames in which each pair's minimum-image distance is < rmax  (the presence rule of
  * compute_atom_two, DDparse.py:148): counts[p] in [0, n_frames]. coords are WRAPPED.
@@ -162,6 +172,16 @@ int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int6
                                      const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
                                      double a, double b, double c, double rmax, double* G,
                                      int64_t M, void* ws, int64_t ws_bytes, dynpy_stream_t stream);
+/* The same with an explicit per-frame filter: mask[p*n_frames + f] != 0 where the pair ROW of frame f passes
+ * the reference's molecule filter (DDparse.py:57-60: `intra` / `inter` compare the per-frame molecule ids, so
+ * a pair changes status in frames where the bond list differs); NULL = no filter.  pair_frames[p] (optional)
+ * receives the number of frames the pair is present in, frame_hit[f] (optional) is set to 1 for every frame
+ * some pair is present in. */
+int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                                     const int32_t* pair_i, const int32_t* pair_j, int64_t n_pairs,
+                                     double a, double b, double c, double rmax, const uint8_t* mask,
+                                     double* G, int64_t* pair_frames, int32_t* frame_hit, int64_t M,
+                                     void* ws, int64_t ws_bytes, dynpy_stream_t stream);
 
 /* ---- spin-rotation -------------------------------------------------------------------------
  * replaces SR_func1 per (molecule, frame) (SRrax.py:438-510) and the backward-difference

@@ -258,6 +258,65 @@ _SR_METHYL_CASES = [("sr_methyl", _SR_ACN % ("methyl", [0, 1, 2, 3, 4], False)),
                     ("sr_ring", _SR_ACN % ("ring", [0, 2], False))]
 
 
+def _write_tinker(path, arr, symbols, title):
+    """Tinker .arc-style blocks: 'nat title' + box line + 'idx sym x y z type conn...' (Angstrom in, the array is
+    bohr); every third frame carries Fortran D exponents, which the reference accepts (d_to_e)."""
+    ang = arr.numpy() * 0.529177
+    with open(path, "w") as fh:
+        for f in range(ang.shape[2]):
+            fh.write("%6d  %s\n   30.000000   30.000000   30.000000   90.000000   90.000000   90.000000\n"
+                     % (len(symbols), title))
+            for a, sym in enumerate(symbols):
+                x, y, z = ang[a, :, f]
+                if f % 3 == 2:
+                    nums = ("%16.8E%16.8E%16.8E" % (x, y, z)).replace("E", "D")
+                else:
+                    nums = "%14.8f%14.8f%14.8f" % (x, y, z)
+                fh.write("%6d  %-3s%s %5d %5d\n" % (a + 1, sym, nums, 1 + a % 3, 2))
+
+
+def _sr_tinker_case(name="sr_tinker_vel"):
+    """Spin-rotation of 6 waters read from a Tinker .arc with EXPLICIT velocities (.vel, parse_vel = True):
+    parse_tinker_md (parseMD.py:177-228) and the branch of prep_SR_uni1 that skips the finite difference."""
+    case = os.path.join(GOLD, name)
+    shutil.rmtree(case, ignore_errors=True)
+    os.makedirs(os.path.join(case, "01"))
+    box = synth.water_box(6, seed=21)
+    nprinted = 26
+    pos = box.frames(0, nprinted)
+    ext = box.frames(-1, nprinted + 1)
+    vel = (ext[:, :, 2:] - ext[:, :, :-2]) / (2 * 0.001)                     # central difference, bohr/ps
+    _write_tinker(os.path.join(case, "01", "water.arc"), pos, box.symbols, "water box")
+    _write_tinker(os.path.join(case, "01", "water.vel"), vel, box.symbols, "velocities")
+    body = PD_TMPL.format(trajs=["01"], nat=box.nat, start=2, end=26, mdp=2, samp=2, celldm=box.celldm, dt=0.001)
+    body = body.replace("MD_format = 'xyz'", "MD_format = 'Tinker'").replace("parse_vel = False", "parse_vel = True")
+    body += "class SpinRotation:\n    mol_type = 'water'\n    nmol = 6\n    C_SR = [36.9, 33.5, 35.5]\n"
+    synth.write_params(os.path.join(case, "params.py"), body)
+    outputs = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv", "{traj}/Jacfs_all.csv",
+               "{traj}/Jacf.csv", "SR-results.csv"]
+    with tempfile.TemporaryDirectory() as tmp:
+        work = os.path.join(tmp, "w")
+        shutil.copytree(case, work)
+        out = refshim.run_cli("-s", "params.py", cwd=work)
+        os.makedirs(os.path.join(case, "ref"))
+        with open(os.path.join(case, "ref", "stdout.txt"), "w") as fh:
+            fh.write(out)
+        for rel in outputs:
+            r = rel.format(traj="01")
+            shutil.copy(os.path.join(work, r), os.path.join(case, "ref", r.replace("/", "__")))
+    print("golden:", name)
+
+
+def _dd_dynamic_cases():
+    """6 waters in a small box: in one sampled frame two molecules touch (an H-H contact inside the bond
+    cut-off), so the per-frame molecule detection merges them there.  'all' pairs do not depend on molecules;
+    'inter' / 'intra' pairs change their status in that frame (DDparse.py:57-60 filters pair ROWS)."""
+    w6 = synth.water_box(6, seed=21)
+    dd = "class Dipolar:\n    identifier = 'H(2)O(1)'\n    pair_type = %r\n    rmax = %r\n"
+    for name, ptype in (("dd_dynamic_all", "all"), ("dd_dynamic_inter", "inter"), ("dd_dynamic_intra", "intra")):
+        _traj_case(name, w6, 26, 2, 26, 2, 2, 0.001, dd % (ptype, 12.0), "-d", ["{traj}/avg-acf.csv", "DD-results.csv"])
+
+
 def _dd_hetero_case():
     """13C-1H dipolar relaxation of the methyl carbon of acetonitrile: analyte_label = 1 (mol-atom index of the
     methyl C), unlike-spin rate formula (ddrax.py:270-271), intramolecular pairs only."""
@@ -282,6 +341,10 @@ def main():
         for name, cls in _SR_METHYL_CASES:
             _traj_case(name, synth.acetonitrile_box(4, seed=4), 22, 1, 22, 1, 1, 0.001, cls, "-s", sr_out)
         return
+    if "--sr-tinker-only" in sys.argv:
+        return _sr_tinker_case()
+    if "--dd-dynamic-only" in sys.argv:
+        return _dd_dynamic_cases()
     if "--dd-hetero-only" in sys.argv:
         return _dd_hetero_case()
     if "--sr-ar-only" in sys.argv:
@@ -315,6 +378,8 @@ def main():
     _traj_case("dd_analyte_label", w8, 30, 1, 30, 1, 1, 0.002, dd_het, "-d", dd_out)
 
     _dd_hetero_case()
+    _dd_dynamic_cases()
+    _sr_tinker_case()
 
     sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
               "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]

@@ -100,7 +100,8 @@ def test_qr_golden_iodide_rates_on_gpu(ops):
 # ------------------------------------------------------------------ DD
 @pytest.mark.parametrize("case,trajs", [("dd_gapless_all", ["01"]), ("dd_gaps_inter", ["01"]),
                                          ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"]),
-                                         ("dd_hetero_13C", ["01"])])
+                                         ("dd_hetero_13C", ["01"]), ("dd_dynamic_all", ["01"]),
+                                         ("dd_dynamic_inter", ["01"]), ("dd_dynamic_intra", ["01"])])
 def test_cli_ddrelax_vs_reference_csv(tmp_path, case, trajs, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-d", work)
@@ -185,10 +186,16 @@ def test_topology_change_is_detected(ops):
     wrapped = ops.wrap(traj.cuda().contiguous(), box.celldm)
     with pytest.raises(RuntimeError, match="topology changes"):
         topology.build_topology(wrapped, box.symbols, (box.celldm,) * 3, 9.5)
+    # dynamic=True: the device scan lists the deviating pair-frames and the host re-indexes those frames —
+    # the molecule number of every atom in every frame must equal the per-frame detection of the oracle
+    ft, _ = topology.build_topology(wrapped, box.symbols, (box.celldm,) * 3, 9.5, dynamic=True)
+    assert ft.frames and 0 not in ft.frames
+    np.testing.assert_array_equal(ft.molecule_ids(np.arange(box.nat)), mol)
 
 
 # ------------------------------------------------------------------ SR
-@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring"])
+@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring",
+                                  "sr_tinker_vel"])
 def test_cli_srrelax_vs_reference_csv(tmp_path, case, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-s", work)

@@ -268,3 +268,32 @@ def test_two_rank_gloo_allreduce(tmp_path):
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2, r.stdout
+
+
+def test_frame_topologies_match_per_frame_molecule_detection():
+    """A trajectory whose bond list changes in one frame (two waters touch): FrameTopologies (static topology +
+    the deviating frames) must give the molecule numbers of the reference's all-frames compute_molecule, and
+    select_molecules must drop the molecules that are not intact in every frame (SRparse.py:171-176)."""
+    from dynpy_b200 import SRparse, synth, topology
+    box = synth.water_box(6, seed=21)
+    pos = box.frames(0, 26).numpy().transpose(2, 0, 1)[1::2]
+    F, A, _ = pos.shape
+    two, mol = orc.atom_two_table(pos, box.symbols, box.celldm, 8.0)
+    per_frame = []
+    for f in range(F):
+        b = two["bond"] & (two["f"] == f)
+        per_frame.append(set(zip(two["i"][b].tolist(), two["j"][b].tolist())))
+    changes = {f: sorted(per_frame[f] ^ per_frame[0]) for f in range(F) if per_frame[f] != per_frame[0]}
+    assert changes, "the fixture is meant to have a frame with an extra contact"
+    b0 = sorted(per_frame[0])
+    base = topology.Topology(A, np.array([x[0] for x in b0]), np.array([x[1] for x in b0]), box.symbols)
+    ft = topology.FrameTopologies(base, changes, F)
+    np.testing.assert_array_equal(ft.molecule_ids(np.arange(A)), mol)
+
+    class SR:
+        mol_type = "water"; nmol = 6
+    keep, nat = SRparse.select_molecules(ft, SR)
+    touched = {a for pairs in changes.values() for ij in pairs for a in ij}
+    want = [m for m in range(6) if not (touched & set(range(3 * m, 3 * m + 3)))]
+    assert [k[0] for k in keep] == want and nat == 3
+    assert [k[2] for k in keep] == [(3 * m, 3 * m + 1, 3 * m + 2) for m in want]

@@ -91,7 +91,8 @@ def _run_dd(case, traj="01"):
 
 @pytest.mark.parametrize("case,trajs", [("dd_gapless_all", ["01"]), ("dd_gaps_inter", ["01"]),
                                          ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"]),
-                                         ("dd_hetero_13C", ["01"])])
+                                         ("dd_hetero_13C", ["01"]), ("dd_dynamic_all", ["01"]),
+                                         ("dd_dynamic_inter", ["01"]), ("dd_dynamic_intra", ["01"])])
 def test_dd_pipeline_vs_reference(case, trajs):
     _, res = _csv(os.path.join(GOLDEN, case, "ref", "DD-results.csv"))
     for k, traj in enumerate(trajs):
@@ -111,15 +112,21 @@ def test_dd_pipeline_vs_reference(case, trajs):
 
 
 # ---------------------------------------------------------------- SR end to end
-@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring"])
+@pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring",
+                                  "sr_tinker_vel"])
 def test_sr_pipeline_vs_reference(case):
     P = load_params(case)
     PD, SR = P.ParseDynamics, P.SpinRotation
-    pos, sym, frames = orc.read_xyz(os.path.join(GOLDEN, case, "01", "traj.xyz"), PD.nat, PD.start_prod,
-                                    PD.end_prod, PD.sample_freq, PD.md_print_freq)
+    sel = (PD.nat, PD.start_prod, PD.end_prod, PD.sample_freq, PD.md_print_freq)
+    vel = None
+    if PD.MD_format == "Tinker":   # explicit velocities; two waters touch in one frame -> they are dropped
+        pos, sym, frames = orc.read_tinker(os.path.join(GOLDEN, case, "01", "water.arc"), *sel)
+        vel, _, _ = orc.read_tinker(os.path.join(GOLDEN, case, "01", "water.vel"), *sel)
+    else:
+        pos, sym, frames = orc.read_xyz(os.path.join(GOLDEN, case, "01", "traj.xyz"), *sel)
     out = orc.sr_pipeline(pos, sym, frames, PD.celldm, PD.timestep, SR.mol_type, SR.nmol, SR.C_SR,
                           identifier=getattr(SR, "identifier", None), methyl_indeces=getattr(SR, "methyl_indeces", None),
-                          global_momentum=getattr(SR, "global_momentum", False))
+                          global_momentum=getattr(SR, "global_momentum", False), vel=vel)
     ref = os.path.join(GOLDEN, case, "ref")
     hdr, rows = _csv(os.path.join(ref, "01__J_cart.csv"))
     a = np.array([[float(x) for x in r[1:]] for r in rows])
