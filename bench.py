@@ -111,10 +111,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def _ref_worker(args):
+_REF_SHARED = {}
+
+
+def _ref_worker(pairs):
+    # the trajectory is inherited through fork (no per-task pickling of the coordinates)
     from oracle import oracle_np as orc
-    w, pairs, L = args
-    return orc.dd_pairs_gapless(w, pairs, L)
+    return orc.dd_pairs_gapless(_REF_SHARED["w"], pairs, _REF_SHARED["L"])
 
 
 def reference_arm(args, wl):
@@ -129,21 +132,22 @@ def reference_arm(args, wl):
     from oracle import oracle_np as orc  # noqa: F401
     cores = os.cpu_count() or 1
     F = wl["frames"] if wl["frames"] <= 100_000 else 100_000
-    nh_sample = 16
+    nh_sample = 32
     box = synth.water_box(wl["nmol"], seed=wl["seed"])
     hmask = torch.tensor([s == "H" for s in box.symbols])
     traj = box.trajectory(F, atom_mask=hmask.nonzero()[:, 0][:nh_sample]).numpy()
     L = box.celldm
     w = np.mod(traj, L)
     pi, pj = h_pairs(nh_sample // 2, wl["pair_type"])
-    per_step = min(len(pi), max(cores * 2, 8))
+    per_step = min(len(pi), max(cores * 8, 8))   # 8 pairs per core and step: a few seconds of work per step
     shards = [list(zip(pi[k:per_step:cores].tolist(), pj[k:per_step:cores].tolist())) for k in range(cores)]
     shards = [s for s in shards if s]
+    _REF_SHARED.update(w=w, L=L)
     times = []
     with mp.get_context("fork").Pool(len(shards)) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            parts = pool.map(_ref_worker, [(w, s, L) for s in shards])
+            parts = pool.map(_ref_worker, shards)
             G = sum(parts)
             t = np.arange(F) * 0.001
             orc.dd_rates(t, G[4] * 2 / nh_sample, G[5] * 2 / nh_sample, G[6] * 2 / nh_sample)
