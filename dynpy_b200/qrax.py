@@ -25,8 +25,7 @@ def read_efg_data(file_path, dtype=None):
 
 
 def _interpolate(a):
-    """pd.Series.interpolate() semantics of wiener_khinchin (qrax.py:149-150), applied only when
-    a series actually holds NaNs (input cleaning, not part of the hot path)."""
+    """pd.Series.interpolate() (linear, forward): interior and trailing NaNs are filled, leading ones stay."""
     ok = ~np.isnan(a)
     if ok.all() or not ok.any():
         return a
@@ -35,6 +34,28 @@ def _interpolate(a):
     a = a.copy()
     a[first:] = np.interp(idx[first:], idx[ok], a[ok])
     return a
+
+
+def _fill_missing(v):
+    """Missing EFG values of one nucleus, v [6, N] = Vxx, Vyy, Vzz, Vxy, Vxz, Vyz (input cleaning, host side;
+    only runs when the series holds NaNs).  wiener_khinchin interpolates the REAL and IMAGINARY parts of each
+    spherical component separately (qrax.py:149-150).  Which samples are missing follows the reference's complex
+    arithmetic (qrax.py:115-130): Re R_2,+-2 = (Vxx - Vyy)/2 is missing where either term is, and `1j * NaN` is
+    NaN in BOTH parts, so a missing Vxy (Vyz) also voids the real part of R_2,+-2 (R_2,+-1).  The five real
+    series are interpolated and an equivalent Cartesian set (Vxx = -Vyy = Re R_22) goes to the device path."""
+    if not np.isnan(v).any():
+        return v
+    out = np.empty_like(v)
+    d = 0.5 * (v[0] - v[1])
+    d[np.isnan(v[3])] = np.nan
+    d = _interpolate(d)
+    out[0], out[1] = d, -d
+    xz = v[4].copy()
+    xz[np.isnan(v[5])] = np.nan
+    out[4] = _interpolate(xz)
+    for c in (2, 3, 5):
+        out[c] = _interpolate(v[c])
+    return out
 
 
 def efg_acf_mean(efg: torch.Tensor, shard=True):
@@ -112,8 +133,7 @@ def QR_module_main(QR, label=None, device=None):
         N = lengths.pop()
         host = np.empty((len(labels), 6, N), dtype=np.float64)
         for k, lab in enumerate(labels):
-            for c, name in enumerate(_COMPS):
-                host[k, c] = _interpolate(series[lab][name].to_numpy(dtype=np.float64))
+            host[k] = _fill_missing(np.stack([series[lab][name].to_numpy(dtype=np.float64) for name in _COMPS]))
         first = series[labels[0]]
         frame = np.mean([series[lab]['frame'].to_numpy(dtype=np.float64) for lab in labels], axis=0)
         tm = np.mean([series[lab]['time'].to_numpy(dtype=np.float64) for lab in labels], axis=0)

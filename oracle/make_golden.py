@@ -89,7 +89,7 @@ class _WithSpectator:
         return torch.cat([self.box.frames(f0, f1), extra.expand(1, 3, f1 - f0)], 0)
 
 
-def _qr_case(name, nnuc, nframes, ntraj, seed, analyte="127I", symbol="I", with_traj0=False):
+def _qr_case(name, nnuc, nframes, ntraj, seed, analyte="127I", symbol="I", with_traj0=False, nan_cells=None):
     case = os.path.join(GOLD, name)
     shutil.rmtree(case, ignore_errors=True)
     os.makedirs(case)
@@ -100,6 +100,17 @@ def _qr_case(name, nnuc, nframes, ntraj, seed, analyte="127I", symbol="I", with_
         with open(csv, "a") as fh:
             fh.write("synthetic,0,1000,0.145,0,%s,1.0,0.0,0.0,0.0,-0.5,0.0,0.0,0.0,-0.5\n" % symbol)
             fh.write("synthetic,1,1000,0.145,77,O,1.0,0.0,0.0,0.0,-0.5,0.0,0.0,0.0,-0.5\n")
+    if nan_cells:   # empty cells -> NaN in read_csv; wiener_khinchin interpolates Re and Im of each R_2m separately
+        with open(csv) as fh:
+            lines = fh.read().split("\n")
+        hdr = lines[0].split(",")
+        for row, cols in nan_cells:
+            t = lines[1 + row].split(",")
+            for c in cols:
+                t[hdr.index(c)] = ""
+            lines[1 + row] = ",".join(t)
+        with open(csv, "w") as fh:
+            fh.write("\n".join(lines))
     synth.write_params(os.path.join(case, "params.py"),
                        "class Quadrupolar:\n    data_set = './efg.csv'\n    analyte = %r\n" % analyte)
     with tempfile.TemporaryDirectory() as tmp:
@@ -326,6 +337,14 @@ def _dd_hetero_case():
                ["{traj}/avg-acf.csv", "DD-results.csv"])
 
 
+# missing EFG values (rows are frame-major, 2 nuclei per frame): a whole tensor, single components (so that
+# Re R_22 = (Vxx - Vyy)/2 is missing where only ONE of its terms is), a run of frames, the last frame
+_ALLV = ["Vxx", "Vxy", "Vxz", "Vyx", "Vyy", "Vyz", "Vzx", "Vzy", "Vzz"]
+_QR_NAN = dict(nnuc=2, nframes=60, ntraj=1, seed=23,
+               nan_cells=[(10, _ALLV), (21, ["Vxx"]), (24, ["Vyy", "Vxz", "Vzx"]), (31, ["Vzz"]), (40, _ALLV), (42, _ALLV),
+                          (44, _ALLV), (57, ["Vxy", "Vyx"]), (118, _ALLV), (119, ["Vyz", "Vzy"])])
+
+
 def main():
     assert refshim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -343,6 +362,8 @@ def main():
         return
     if "--sr-tinker-only" in sys.argv:
         return _sr_tinker_case()
+    if "--qr-nan-only" in sys.argv:
+        return _qr_case("qr_nan", **_QR_NAN)
     if "--dd-dynamic-only" in sys.argv:
         return _dd_dynamic_cases()
     if "--dd-hetero-only" in sys.argv:
@@ -365,6 +386,7 @@ def main():
 
     _qr_case("qr_small", nnuc=3, nframes=64, ntraj=2, seed=1, with_traj0=True)
     _qr_case("qr_odd", nnuc=2, nframes=81, ntraj=1, seed=11)
+    _qr_case("qr_nan", **_QR_NAN)
 
     w8 = synth.water_box(8, seed=2, drift=0.02)
     dd = "class Dipolar:\n    identifier = 'H(2)O(1)'\n    pair_type = %r\n    rmax = %r\n"

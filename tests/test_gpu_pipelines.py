@@ -58,7 +58,7 @@ def _run_cli(flag, work, stdin="y\n"):
 
 
 # ------------------------------------------------------------------ QR
-@pytest.mark.parametrize("case", ["qr_small", "qr_odd"])
+@pytest.mark.parametrize("case", ["qr_small", "qr_odd", "qr_nan"])
 def test_cli_qrelax_vs_reference_csv(tmp_path, case, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-q", work)

@@ -297,3 +297,25 @@ def test_frame_topologies_match_per_frame_molecule_detection():
     want = [m for m in range(6) if not (touched & set(range(3 * m, 3 * m + 3)))]
     assert [k[0] for k in keep] == want and nat == 3
     assert [k[2] for k in keep] == [(3 * m, 3 * m + 1, 3 * m + 2) for m in want]
+
+
+def test_qr_missing_values_follow_reference_complex_arithmetic():
+    """qrax._fill_missing (host-side input cleaning of the QR driver): the filled Cartesian set must give the
+    same five spherical series as interpolating Re/Im of the reference's R_2m — including `1j * NaN` voiding the
+    real part (fixture qr_nan, whose ACFs the oracle reproduces from the reference's output)."""
+    from dynpy_b200 import qrax
+    rows = orc.read_efg_csv(os.path.join(GOLDEN, "qr_nan", "efg.csv"))
+    names = ("Vxx", "Vyy", "Vzz", "Vxy", "Vxz", "Vyz")
+    for lab in (0, 1):
+        m = rows["label"] == lab
+        v = np.stack([rows[k][m] for k in names])
+        assert np.isnan(v).any()
+        f = qrax._fill_missing(v)
+        assert not np.isnan(f).any()
+        want = orc.qr_spatial({k: v[i] for i, k in enumerate(names)})
+        want = [orc.interpolate_nan(np.real(r)) + 1j * orc.interpolate_nan(np.imag(r)) for r in want]
+        got = orc.qr_spatial({k: f[i] for i, k in enumerate(names)})
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-15)
+    clean = np.arange(12.0).reshape(6, 2)
+    assert qrax._fill_missing(clean) is clean

@@ -59,7 +59,7 @@ def test_wk_equals_direct_and_interpolates():
 
 
 # ---------------------------------------------------------------- QR end to end
-@pytest.mark.parametrize("case", ["qr_small", "qr_odd"])
+@pytest.mark.parametrize("case", ["qr_small", "qr_odd", "qr_nan"])
 def test_qr_pipeline_vs_reference(case):
     rows = orc.read_efg_csv(os.path.join(GOLDEN, case, "efg.csv"))
     res, acfs = orc.qr_pipeline(rows, "127I")
