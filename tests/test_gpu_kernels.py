@@ -299,6 +299,47 @@ def test_dd_full_size_properties(ops):
     np.testing.assert_allclose(G0, ref, rtol=1e-10)
 
 
+def test_dd_cfg5_frame_count_properties(ops):
+    """cfg5 frame count (1e6 frames, M = 2^21, 512-point column transforms): lag 0 and a few scattered lags of
+    the summed ACFs against direct O(N) sums of independently formed series, and additivity over pair sets."""
+    from dynpy_b200 import synth
+    F = 1_000_000
+    box = synth.water_box(8, seed=5).to("cuda")
+    hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
+    L = box.celldm
+    w = ops.wrap(box.trajectory(F, chunk=1 << 16, atom_mask=hidx), L)
+    i, j = np.triu_indices(16, k=1)
+    i, j = i[:9], j[:9]
+    pi, pj = dev(i, torch.int32), dev(j, torch.int32)
+    cell = (L, L, L)
+    M = ops.fft_length(F)
+    assert M == 1 << 21
+    whole = ops.dd_pairs_to_spectrum(w, pi, pj, cell, M=M)
+    part = ops.dd_pairs_to_spectrum(w, pi[:4], pj[:4], cell, M=M)
+    part = ops.dd_pairs_to_spectrum(w, pi[4:], pj[4:], cell, M=M, spectrum=part)
+    scale = whole.abs().amax(dim=1, keepdim=True)
+    assert float(((whole - part).abs() / scale).max()) < 1e-12
+    G = ops.ifft_acf(whole, F, 1.0 / (float(M) * F))
+    a = w[torch.as_tensor(i, device="cuda")]
+    b = w[torch.as_tensor(j, device="cuda")]
+    d = a - b
+    d = d - L * torch.round(d / L)
+    r2 = (d * d).sum(dim=1)
+    r3 = r2 ** -1.5
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    kf = np.sqrt(4 * np.pi / 5)
+    y20 = (0.25 * np.sqrt(5 / np.pi) * (3 * z * z / r2 - 1)).to(torch.complex128)
+    y21 = -0.5 * np.sqrt(15 / (2 * np.pi)) * z * torch.complex(x, y) / r2
+    y22 = 0.25 * np.sqrt(15 / (2 * np.pi)) * torch.complex(x, y) ** 2 / r2
+    dr3 = (r3 - r3.mean(dim=1, keepdim=True)).to(torch.complex128)
+    series = [y20, y21, y22, dr3, kf * r3 * y20, kf * r3 * y21, kf * r3 * y22]
+    for lag in (0, 1, 777, 500_000, 999_999):
+        for c, sr in enumerate(series):
+            ref = float((sr[:, :F - lag].conj() * sr[:, lag:]).real.sum()) / F
+            got = float(G[c, lag])
+            assert abs(got - ref) <= 1e-10 * float(G[c].abs().max()), (lag, c, got, ref)
+
+
 # ---------------------------------------------------------------- J(omega) / cutoff (SURVEY §8f rank 4)
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 60, 316, 777, 1000, 1009, 4096, 65536, 99991, 100000])
 def test_dft_any_length_vs_numpy(ops, n):
