@@ -319,3 +319,37 @@ def test_neighbors_larger_box_vs_oracle(ops):
     assert atom["symbol"].tolist() == [c[0] for c in clusters[6]]
     np.testing.assert_array_equal(atom[["x", "y", "z"]].to_numpy(), np.array([c[1:4] for c in clusters[6]]))
     assert len(atom) >= 2 * (6 * 3 + 1)
+
+
+# ------------------------------------------------------------------ sharded runs (2 ranks on one GPU, gloo)
+@pytest.mark.parametrize("flag,case,files", [
+    ("-d", "dd_gaps_inter", ["01/avg-acf.csv", "DD-results.csv"]),
+    ("-d", "dd_dynamic_intra", ["01/avg-acf.csv", "DD-results.csv"]),
+    ("-s", "sr_methane", ["01/Jacf.csv", "01/J_cart.csv", "SR-results.csv"]),
+    ("-q", "qr_small", ["efg-I-acfs.csv", "efg-I-relax.csv"])])
+def test_cli_two_ranks_equal_one_rank(tmp_path, flag, case, files, ops):
+    """The same CLI under torchrun with two ranks (pairs / molecules / nuclei sharded, one all-reduce; gloo so
+    that both ranks can share the single GPU of the test box) must write what the single-process run writes."""
+    one = _workdir(tmp_path / "one", case)
+    _run_cli(flag, one)
+    two = _workdir(tmp_path / "two", case)
+    env = dict(os.environ, PYTHONPATH=ROOT, DYNPY_DIST_BACKEND="gloo", OMP_NUM_THREADS="1")
+    port = 29000 + (os.getpid() * 7 + len(case)) % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "dynpy", flag, "params.py"],
+                       cwd=two, input="y\n", text=True, capture_output=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for f in files:
+        h1, r1 = _csv(os.path.join(one, f))
+        h2, r2 = _csv(os.path.join(two, f))
+        assert h1 == h2 and len(r1) == len(r2), f
+        for a, b in zip(r1, r2):
+            for x, y in zip(a, b):
+                try:
+                    fx, fy = float(x), float(y)
+                except ValueError:
+                    assert x == y
+                    continue
+                if np.isnan(fx) and np.isnan(fy):
+                    continue
+                assert abs(fx - fy) <= 1e-9 * max(abs(fx), 1e-30) + 1e-18, (f, x, y)
