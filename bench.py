@@ -278,7 +278,7 @@ def native_arm(args, wl):
     staging = torch.empty_like(raw)
 
     def e2e_step():
-        staging.copy_(host_raw, non_blocking=True)
+        dist.h2d_sharded(host_raw, staging)   # each rank copies 1/world over PCIe, blocks exchanged over NVLink
         Gd, r = step(staging)
         host_G.copy_(Gd, non_blocking=True)
         torch.cuda.current_stream().synchronize()

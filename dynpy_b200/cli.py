@@ -79,6 +79,8 @@ def main(argv=None):
             from . import DDparse, dist
             dist.init_from_env()
             DDparse.DD_module_main(dynpy_params.ParseDynamics, dynpy_params.Dipolar)
+    if 'dynpy_b200.dist' in sys.modules:
+        sys.modules['dynpy_b200.dist'].shutdown()   # multi-rank runs: tear the process group down cleanly
 
 
 if __name__ == "__main__":

@@ -62,6 +62,23 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def h2d_sharded(host: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Host -> device copy of an array every rank needs in full (the coordinates): each rank moves 1/world of
+    dim 0 over ITS host link and the blocks are then exchanged GPU to GPU (one broadcast per block: NVLink),
+    instead of every rank pulling the whole array through PCIe.  Single process: a plain copy."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1 or host.shape[0] < world:
+        out.copy_(host, non_blocking=True)
+        return out
+    rank = dist.get_rank()
+    n = host.shape[0]
+    cuts = [(n * r) // world for r in range(world + 1)]
+    out[cuts[rank]:cuts[rank + 1]].copy_(host[cuts[rank]:cuts[rank + 1]], non_blocking=True)
+    for r in range(world):
+        dist.broadcast(out[cuts[r]:cuts[r + 1]], src=r)
+    return out
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

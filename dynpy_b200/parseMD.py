@@ -101,6 +101,30 @@ def _read_blocks_py(path, nat, header_lines, cols, printed):
     return symbols, out
 
 
+def _load_frames(path, nat, header_lines, cols, printed, device):
+    """(symbols, coords [A, 3, F] on `device`) of the printed frames.  With several ranks every rank parses only
+    its block of frames (the text is the expensive part), copies it over its own host link and the blocks are
+    exchanged GPU to GPU, so that every rank ends up with the whole trajectory."""
+    import torch.distributed as tdist
+
+    from . import dist
+    rank, world = dist.rank_world()
+    F = len(printed)
+    if world == 1 or device.type != "cuda" or F < world:
+        sym, xyz = _read_blocks(path, nat, header_lines, cols, printed, 0.529177, pin=True)
+        # [F][A][3] (pinned host) -> device -> the kernels' [A][3][F] layout (transpose on the device)
+        return sym, xyz.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
+    cuts = [(F * r) // world for r in range(world + 1)]
+    sym, mine = _read_blocks(path, nat, header_lines, cols, printed[cuts[rank]:cuts[rank + 1]], 0.529177, pin=True)
+    full = torch.empty((F, nat, 3), dtype=torch.float64, device=device)
+    full[cuts[rank]:cuts[rank + 1]].copy_(mine, non_blocking=True)
+    for r in range(world):
+        tdist.broadcast(full[cuts[r]:cuts[r + 1]], src=r)
+    box = [sym]
+    tdist.broadcast_object_list(box, src=0)   # symbols of the first printed frame, as in the single-process run
+    return box[0], full.permute(1, 2, 0).contiguous()
+
+
 def _find(traj_dir, token, what):
     try:
         return [f for f in os.listdir(traj_dir) if token in f][0]
@@ -122,11 +146,11 @@ def PARSE_MD(PD, traj, device=None):
     printed = _select_frames(PD.start_prod, PD.end_prod, PD.sample_freq)
     if fmt == "xyz":
         name = _find(traj_dir, ".xyz", ".xyz")
-        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (0, 1, 2, 3), printed, 0.529177, pin=True)
+        header, cols = 2, (0, 1, 2, 3)
     elif fmt == "Tinker":
         name = _find(traj_dir, "arc", ".arc")
         print("reading " + name)
-        sym, xyz = _read_blocks(os.path.join(traj_dir, name), PD.nat, 2, (1, 2, 3, 4), printed, 0.529177, pin=True)
+        header, cols = 2, (1, 2, 3, 4)
     elif fmt == "QE":
         if 'symbols' not in PD.__dict__.keys():
             print("Error: Missing required input variable symbols in class ParseDynamics for parsing QE.")
@@ -137,13 +161,10 @@ def PARSE_MD(PD, traj, device=None):
         print("MD_format not provided or not recognized. Implemented formats are 'QE', 'Tinker', and 'xyz'. "
               "Do you need to parse MD trajectories?")
         sys.exit(2)
-    # [F][A][3] (pinned host) -> device -> the kernels' [A][3][F] layout (transpose on the device)
-    pos = xyz.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
+    sym, pos = _load_frames(os.path.join(traj_dir, name), PD.nat, header, cols, printed, device)
     frames = printed.astype(np.int64) * int(PD.md_print_freq)
     vel = None
     if PD.parse_vel:
         vname = _find(traj_dir, ".vel", ".vel")
-        cols = (0, 1, 2, 3) if fmt == "xyz" else (1, 2, 3, 4)
-        _, v = _read_blocks(os.path.join(traj_dir, vname), PD.nat, 2, cols, printed, 0.529177, pin=True)
-        vel = v.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
+        _, vel = _load_frames(os.path.join(traj_dir, vname), PD.nat, header, cols, printed, device)
     return Trajectory(pos=pos, symbols=sym, frames=frames, vel=vel)

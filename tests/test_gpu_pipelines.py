@@ -326,6 +326,7 @@ def test_neighbors_larger_box_vs_oracle(ops):
     ("-d", "dd_gaps_inter", ["01/avg-acf.csv", "DD-results.csv"]),
     ("-d", "dd_dynamic_intra", ["01/avg-acf.csv", "DD-results.csv"]),
     ("-s", "sr_methane", ["01/Jacf.csv", "01/J_cart.csv", "SR-results.csv"]),
+    ("-s", "sr_tinker_vel", ["01/Jacf.csv", "01/J_cart.csv", "01/molax.csv", "SR-results.csv"]),
     ("-q", "qr_small", ["efg-I-acfs.csv", "efg-I-relax.csv"])])
 def test_cli_two_ranks_equal_one_rank(tmp_path, flag, case, files, ops):
     """The same CLI under torchrun with two ranks (pairs / molecules / nuclei sharded, one all-reduce; gloo so
@@ -352,4 +353,4 @@ def test_cli_two_ranks_equal_one_rank(tmp_path, flag, case, files, ops):
                     continue
                 if np.isnan(fx) and np.isnan(fy):
                     continue
-                assert abs(fx - fy) <= 1e-9 * max(abs(fx), 1e-30) + 1e-18, (f, x, y)
+                assert abs(fx - fy) <= 1e-9 * max(abs(fx), 1e-30) + 1e-13, (f, x, y)  # the `err` row of one trajectory is rounding noise
