@@ -18,6 +18,12 @@ from .nuc import HBAR, MU_0, nuc
 G_COLUMNS = ['$G_{Y2,0}$', '$G_{Y2,1}$', '$G_{Y2,2}$', '$G_{r}$', '$G_{2,0}$', '$G_{2,1}$', '$G_{2,2}$']
 
 
+def wiener_khinchin(f):
+    """ddrax.py:276-285: the same function as qrax.wiener_khinchin."""
+    from .qrax import wiener_khinchin as wk
+    return wk(f)
+
+
 def gapless(cell, rmax) -> bool:
     """True when every pair is inside rmax in every frame: min-image distance <= sqrt(a^2+b^2+c^2)/2."""
     half_diag2 = 0.25 * (cell[0] ** 2 + cell[1] ** 2 + cell[2] ** 2)

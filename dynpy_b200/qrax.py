@@ -58,6 +58,28 @@ def _fill_missing(v):
     return out
 
 
+def wiener_khinchin(f):
+    """qrax.py:147-156 (== ddrax.py:276-285, SRrax.py:216-225) for one series or a batch [S, N]: NaNs of the
+    real and imaginary parts are interpolated separately (host, only when present), then the biased linear ACF
+    real(ifft(|fft(f, 2N)|^2))[:N] / N comes from the CUDA Wiener–Khinchin kernels.  numpy in -> numpy out,
+    CUDA tensor in -> CUDA tensor out (real or complex input)."""
+    as_numpy = not isinstance(f, torch.Tensor)
+    t = torch.as_tensor(np.asarray(f)) if as_numpy else f
+    one = t.dim() == 1
+    if one:
+        t = t[None]
+    re = (t.real if t.is_complex() else t).to(torch.float64)
+    im = t.imag.to(torch.float64) if t.is_complex() else None
+    if bool(torch.isnan(re).any()) or (im is not None and bool(torch.isnan(im).any())):
+        re = torch.from_numpy(np.stack([_interpolate(r) for r in re.cpu().numpy()]))
+        if im is not None:
+            im = torch.from_numpy(np.stack([_interpolate(r) for r in im.cpu().numpy()]))
+    dev = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    acf = ops.wk_acf_each(re.to(dev).contiguous(), None if im is None else im.to(dev).contiguous())
+    acf = acf[0] if one else acf
+    return acf.cpu().numpy() if as_numpy else acf
+
+
 def efg_acf_mean(efg: torch.Tensor, shard=True):
     """efg [S,6,N] cuda -> mean over the S nuclei of the five ACFs f_{2,m}, m=-2..2: [5,N] cuda
     (cart_to_spatial + groupby('label').apply(correlate) + mean over labels, qrax.py:59-63)."""

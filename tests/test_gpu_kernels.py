@@ -427,3 +427,20 @@ def test_spectral_density_mirrors_vs_reference_vectors(ops):
         ddrax.dipolar(None, "1H", "1H", extr_narr=False)
     one = ddrax.dipolar(2.5e-3, "1H", "1H", single_J=True)
     assert list(one.index) == ["1H"] and one.shape == (1, 1)
+
+
+def test_wiener_khinchin_mirror_vs_reference_vectors(ops):
+    """qrax.wiener_khinchin / ddrax.wiener_khinchin (the reference's call-site name) against outputs of the
+    reference's own function: complex, complex with NaNs (interpolated per part), real; numpy and tensor input."""
+    from dynpy_b200 import ddrax, qrax
+    g = np.load(os.path.join(GOLDEN, "leaf_vectors.npz"))
+    for tag, fn in (("wk", qrax.wiener_khinchin), ("wk_nan", qrax.wiener_khinchin), ("wk_real", ddrax.wiener_khinchin)):
+        x, want = g[tag + "_in"], g[tag + "_out"]
+        got = fn(x)
+        assert isinstance(got, np.ndarray) and got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    x = g["wk_in"]
+    t = torch.as_tensor(np.stack([x, 2 * x])).cuda()
+    out = qrax.wiener_khinchin(t)
+    assert out.is_cuda and out.shape == (2, len(x))
+    assert np.abs(out[1].cpu().numpy() - 4 * g["wk_out"]).max() <= 1e-12 * 4 * np.abs(g["wk_out"]).max()
