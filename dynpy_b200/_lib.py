@@ -34,6 +34,7 @@ SIGNATURES = {
     "dynpy_wrap_f64": (i32, [p, p, i64, f64, p]),
     "dynpy_pdist_workspace_bytes": (i64, [i64]),
     "dynpy_pdist_ortho_f64": (i32, [p, p, p, i64, i64, f64, f64, f64, p, f64, p, p, p, p, p, p, p, p, p, i64, p]),
+    "dynpy_cart_to_dipolar_f64": (i32, [p, p, p, p, i64, p, p]),
     "dynpy_supercell_f64": (i32, [p, i64, i64, i64, f64, p, p]),
     "dynpy_topology_check_f64": (i32, [p, i64, i64, p, f64, p, f64, f64, f64, f64, p, p]),
     "dynpy_topology_events_f64": (i32, [p, i64, i64, p, f64, p, f64, f64, f64, f64, p, i64, p, p]),

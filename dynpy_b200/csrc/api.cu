@@ -370,6 +370,20 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
     return DYNPY_OK;
 }
 
+int dynpy_cart_to_dipolar_f64(const double* dx, const double* dy, const double* dz, const double* dr, int64_t n,
+                              double* out, dynpy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || (n > 0 && (!dx || !dy || !dz || !dr || !out))) {
+        set_error("dynpy_cart_to_dipolar_f64: invalid arguments");
+        return DYNPY_ERR_INVALID;
+    }
+    DeviceState* d;
+    int rc = get_device_state(&d, st);
+    if (rc) return rc;
+    DYNPY_CHECK(launch_cart_to_dipolar(dx, dy, dz, dr, n, out, d->n_sm, st), "cart_to_dipolar");
+    return DYNPY_OK;
+}
+
 int dynpy_supercell_f64(const double* coords, int64_t n_atoms, int64_t n_frames, int64_t frame, double a, double* out,
                         dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;

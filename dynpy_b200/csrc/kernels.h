@@ -21,6 +21,8 @@ cudaError_t launch_pdist(const double* ux, const double* uy, const double* uz, i
 cudaError_t launch_supercell(const double* pos, i64 n, i64 F, i64 frame, double a, double* out, cudaStream_t st);
 cudaError_t launch_dd_words(const double* X, i64 A, i64 N, const int* pi, const int* pj, i64 pair0, i64 n_pairs,
                             i64 items, double a, double b, double c, double* Z, double* bias, cudaStream_t st);
+cudaError_t launch_cart_to_dipolar(const double* dx, const double* dy, const double* dz, const double* dr, i64 n,
+                                   double* out, int n_sm, cudaStream_t st);
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
                                  double b, double c, double rmax, i64* counts, int* frame_hit, cudaStream_t st);
 cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,

@@ -292,6 +292,32 @@ cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* r
     return cudaGetLastError();
 }
 
+// ddrax.cart_to_dipolar_from_df (ddrax.py:110-126) as a stand-alone call: pair vectors -> the 11 real words
+// r^-3, Y20, Re/Im Y21, Re/Im Y22, F20, Re/Im F21, Re/Im F22 (rows of out[11][n] in that order)
+__global__ void k_cart_to_dipolar(const double* __restrict__ dx, const double* __restrict__ dy,
+                                  const double* __restrict__ dz, const double* __restrict__ dr, i64 n,
+                                  double* __restrict__ out) {
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (i64)gridDim.x * blockDim.x) {
+        const double r = dr[k];
+        const DDWords w = dd_words(dx[k], dy[k], dz[k], r * r);
+        out[k] = w.r3;
+        out[n + k] = w.y20;
+        out[2 * n + k] = w.y21r; out[3 * n + k] = w.y21i;
+        out[4 * n + k] = w.y22r; out[5 * n + k] = w.y22i;
+        out[6 * n + k] = w.f20;
+        out[7 * n + k] = w.f21r; out[8 * n + k] = w.f21i;
+        out[9 * n + k] = w.f22r; out[10 * n + k] = w.f22i;
+    }
+}
+cudaError_t launch_cart_to_dipolar(const double* dx, const double* dy, const double* dz, const double* dr, i64 n,
+                                   double* out, int n_sm, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 16 * n_sm) blocks = 16 * n_sm;
+    k_cart_to_dipolar<<<(unsigned)blocks, 256, 0, st>>>(dx, dy, dz, dr, n, out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ ragged dipolar series
 // One CTA per pair: compress the frames in which the pair is present (r2 < rmax^2) into 7
 // complex series of length N_p (Y20, Y21, Y22, r^-3, F20, F21, F22; real ones with zero

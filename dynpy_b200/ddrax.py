@@ -24,6 +24,24 @@ def wiener_khinchin(f):
     return wk(f)
 
 
+DIPOLAR_COLUMNS = ["$r^{-3}$", "$Y_{2,0}$", "$Y_{2,1}$", "$Y_{2,2}$", "$F_{2,0}$", "$F_{2,1}$", "$F_{2,2}$"]
+
+
+def cart_to_dipolar_from_df(atom_two):
+    """ddrax.py:110-126 with the reference's signature: a table with columns dx, dy, dz, dr, time, label0, label1
+    -> DataFrame(time, label0, label1, r^-3, Y_2m, F_2m) (Y_21, Y_22, F_21, F_22 complex).  The words come from
+    the CUDA kernel (Cartesian closed forms of the angle formulas, <= 2e-13 relative)."""
+    import pandas as pd
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cols = [torch.tensor(np.asarray(atom_two[c], dtype=np.float64), device=dev)
+            for c in ("dx", "dy", "dz", "dr")]
+    w = ops.cart_to_dipolar(*cols).cpu().numpy()
+    return pd.DataFrame.from_dict({"time": atom_two['time'], "label0": atom_two['label0'], "label1": atom_two['label1'],
+                                   "$r^{-3}$": w[0], "$Y_{2,0}$": w[1], "$Y_{2,1}$": w[2] + 1j * w[3],
+                                   "$Y_{2,2}$": w[4] + 1j * w[5], "$F_{2,0}$": w[6], "$F_{2,1}$": w[7] + 1j * w[8],
+                                   "$F_{2,2}$": w[9] + 1j * w[10]})
+
+
 def gapless(cell, rmax) -> bool:
     """True when every pair is inside rmax in every frame: min-image distance <= sqrt(a^2+b^2+c^2)/2."""
     half_diag2 = 0.25 * (cell[0] ** 2 + cell[1] ** 2 + cell[2] ** 2)

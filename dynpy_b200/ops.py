@@ -189,6 +189,19 @@ def pdist_ortho(ux, uy, uz, a, b, c, index, dmax=8.0, stride=1):
     return tuple(t[:k] for t in f) + tuple(t[:k] for t in g)
 
 
+def cart_to_dipolar(dx, dy, dz, dr):
+    """Pair vectors [n] -> [11, n]: r^-3, Y20, Re/Im Y21, Re/Im Y22, F20, Re/Im F21, Re/Im F22."""
+    lib = _lib.load()
+    dx, dy, dz, dr = (_chk(t, torch.float64, nm) for t, nm in ((dx, "dx"), (dy, "dy"), (dz, "dz"), (dr, "dr")))
+    n = dx.numel()
+    out = torch.empty((11, n), dtype=torch.float64, device=dx.device)
+    with torch.cuda.device(dx.device):
+        rc = lib.dynpy_cart_to_dipolar_f64(dx.data_ptr(), dy.data_ptr(), dz.data_ptr(), dr.data_ptr(), n, out.data_ptr(),
+                                           _stream())
+    _lib.check(rc, "dynpy_cart_to_dipolar_f64")
+    return out
+
+
 def supercell(coords, frame: int, a: float):
     """[A,3,F] raw coords -> [3, 27A]: the 27 periodic images of frame index `frame` (neighbors._worker)."""
     lib = _lib.load()

@@ -118,6 +118,12 @@ int dynpy_pdist_ortho_f64(const double* ux, const double* uy, const double* uz, 
                           int64_t* atom0, int64_t* atom1, int64_t* projection, int64_t* count,
                           void* ws, int64_t ws_bytes, dynpy_stream_t stream);
 
+/* ddrax.cart_to_dipolar_from_df (ddrax.py:110-126) as a stand-alone call: n pair vectors (dx, dy, dz, dr) ->
+ * out[11][n] = r^-3, Y20, Re Y21, Im Y21, Re Y22, Im Y22, F20, Re F21, Im F21, Re F22, Im F22 (Cartesian
+ * closed forms of the angle formulas; the fused dipolar path forms the same words on the fly). */
+int dynpy_cart_to_dipolar_f64(const double* dx, const double* dy, const double* dz, const double* dr,
+                              int64_t n, double* out, dynpy_stream_t stream);
+
 /* 3x3x3 block of periodic images of one frame (neighbors._worker, neighbors.py:160-199):
  * coords [n_atoms][3][n_frames] (raw) -> out[3][27*n_atoms]; super atom p*n_atoms + l is atom l
  * shifted by (i, j, k)*a with image number p = 9(i+1) + 3(j+1) + (k+1), i, j, k in {-1, 0, 1}. */

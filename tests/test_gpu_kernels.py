@@ -444,3 +444,19 @@ def test_wiener_khinchin_mirror_vs_reference_vectors(ops):
     out = qrax.wiener_khinchin(t)
     assert out.is_cuda and out.shape == (2, len(x))
     assert np.abs(out[1].cpu().numpy() - 4 * g["wk_out"]).max() <= 1e-12 * 4 * np.abs(g["wk_out"]).max()
+
+
+def test_cart_to_dipolar_from_df_vs_reference_vectors(ops):
+    """ddrax.cart_to_dipolar_from_df (call-site signature) against the reference's numba ufuncs."""
+    import pandas as pd
+    from dynpy_b200 import ddrax
+    g = np.load(os.path.join(GOLDEN, "leaf_vectors.npz"))
+    d = g["dd_in"]
+    df = pd.DataFrame({"dx": d[0], "dy": d[1], "dz": d[2], "dr": d[3], "time": np.arange(d.shape[1], dtype=float),
+                       "label0": 0, "label1": 1})
+    F = ddrax.cart_to_dipolar_from_df(df)
+    assert list(F.columns) == ["time", "label0", "label1"] + ddrax.DIPOLAR_COLUMNS
+    for col, key in zip(ddrax.DIPOLAR_COLUMNS, ("dd_r-3", "dd_Y20", "dd_Y21", "dd_Y22", "dd_F20", "dd_F21", "dd_F22")):
+        want = g[key]
+        got = F[col].to_numpy()
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), col
