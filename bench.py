@@ -394,7 +394,7 @@ def other_arm(args, wl):
                                     1000.0, want_omega=False, want_axes=False)
             spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
             for c in range(3):
-                ops.wk_acf_sum(J[:, c, :].contiguous(), pack_real_pairs=True, M=M, spectrum=spec[c])
+                ops.wk_acf_sum(J[:, c, :], pack_real_pairs=True, M=M, spectrum=spec[c])
             dist.allreduce_sum_(spec)
             acf = ops.ifft_acf(spec, F, 1.0 / (float(M) * F * nmol))
             return acf, ops.simpson(acf, tdev, "cartwright").cpu()

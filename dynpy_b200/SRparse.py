@@ -128,7 +128,7 @@ def sr_trajectory(tr, PD, SR, simpson_mode, per_molecule_acfs=True):
     spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
     for c in range(3):
         if hi > lo:
-            ops.wk_acf_sum(J[lo:hi, c, :].contiguous(), pack_real_pairs=True, M=M, spectrum=spec[c])
+            ops.wk_acf_sum(J[lo:hi, c, :], pack_real_pairs=True, M=M, spectrum=spec[c])  # strided view, no copy
     dist.allreduce_sum_(spec)
     acf_mean = ops.ifft_acf(spec, F, 1.0 / (float(M) * float(F) * float(nmol)))
     tdev = torch.from_numpy(frames).to(dev).to(torch.float64) * float(PD.timestep)

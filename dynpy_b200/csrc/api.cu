@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/dynpy_b200.h"
@@ -25,6 +26,7 @@ int fail_cuda(cudaError_t e, const char* where) {
 }
 
 static DeviceState g_dev[64];
+static std::mutex g_dev_mutex;   // first use of a device (twiddle table) and the profiling lists
 
 // ---- profiling hooks -------------------------------------------------------------------
 struct ProfState {
@@ -41,12 +43,14 @@ static cudaEvent_t prof_event() {
 }
 void prof_begin(int cls, cudaStream_t st) {
     if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, st);
     g_prof.ev[cls].push_back(e);
 }
 void prof_end(int cls, cudaStream_t st) {
     if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, st);
     g_prof.ev[cls].push_back(e);
@@ -60,6 +64,7 @@ int get_device_state(DeviceState** out, cudaStream_t st) {
         return DYNPY_ERR_NO_DEVICE;
     }
     DeviceState& d = g_dev[dev];
+    std::lock_guard<std::mutex> lock(g_dev_mutex);  // calls from several host threads may race on the first use
     if (!d.ready) {
         cudaDeviceProp prop;
         DYNPY_CHECK(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
@@ -118,6 +123,7 @@ int dynpy_profile_enable(int on) {
 int dynpy_profile_read(double* ms_host, int64_t* launches_host) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return fail_cuda(e, "profile sync");
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     for (int c = 0; c < PROF_NCLS; ++c) {
         double tot = 0.0;
         auto& v = g_prof.ev[c];

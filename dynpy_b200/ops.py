@@ -28,6 +28,17 @@ def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def _chk_rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D float64 CUDA tensor whose rows are contiguous (any row stride: a [:, c, :] view of [S, 3, N] works)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DynpyError("%s must be a CUDA tensor (dynpy_b200 has no CPU path)" % name)
+    if t.dtype != torch.float64 or t.dim() != 2:
+        raise _lib.DynpyError("%s must be a 2-D float64 tensor" % name)
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise _lib.DynpyError("%s: the series (last axis) must be contiguous" % name)
+    return t
+
+
 def workspace(device, nbytes: int) -> torch.Tensor:
     """Grow-only per-device scratch buffer (uint8)."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
@@ -69,11 +80,12 @@ def _fft_ws(M: int, n_fft: int, device, budget: int = 2 << 30):
 def wk_acf_sum(re, im=None, pack_real_pairs=False, scale=None, M=None, spectrum=None):
     """spectrum[M] += sum_s |FFT_M(series_s)|^2 for series ``re[s] (+ i im[s])`` of shape [S, N]."""
     lib = _lib.load()
-    re = _chk(re, torch.float64, "re")
+    re = _chk_rows(re, "re")
     S, N = re.shape
+    stride = re.stride(0) if S > 1 else N
     if im is not None:
-        im = _chk(im, torch.float64, "im")
-        assert im.shape == re.shape
+        im = _chk_rows(im, "im")
+        assert im.shape == re.shape and (S == 1 or im.stride(0) == stride)
     if scale is not None:
         scale = _chk(scale, torch.float64, "scale")
     M = fft_length(N) if M is None else int(M)
@@ -83,7 +95,7 @@ def wk_acf_sum(re, im=None, pack_real_pairs=False, scale=None, M=None, spectrum=
     with torch.cuda.device(re.device):
         n_fft = (S + 1) // 2 if pack_real_pairs else S
         ws, wsb = _fft_ws(M, n_fft, re.device)
-        rc = lib.dynpy_wk_acf_sum_f64(re.data_ptr(), im.data_ptr() if im is not None else None, S, N, N,
+        rc = lib.dynpy_wk_acf_sum_f64(re.data_ptr(), im.data_ptr() if im is not None else None, S, N, stride,
                                       1 if pack_real_pairs else 0, scale.data_ptr() if scale is not None else None,
                                       spectrum.data_ptr(), M, ws.data_ptr() if ws is not None else None, wsb, _stream())
     _lib.check(rc, "dynpy_wk_acf_sum_f64")

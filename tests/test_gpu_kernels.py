@@ -460,3 +460,17 @@ def test_cart_to_dipolar_from_df_vs_reference_vectors(ops):
         want = g[key]
         got = F[col].to_numpy()
         assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), col
+
+
+def test_wk_acf_sum_strided_rows(ops):
+    """Series given as a strided view (component c of J[mol][3][frame]) must give exactly what a contiguous copy
+    gives — the spin-rotation driver passes such views to avoid three copies of J."""
+    torch.manual_seed(3)
+    J = torch.randn((7, 3, 1500), dtype=torch.float64, device="cuda")
+    for c in range(3):
+        for pack in (True, False):
+            a = ops.wk_acf_sum(J[:, c, :], pack_real_pairs=pack)
+            b = ops.wk_acf_sum(J[:, c, :].contiguous(), pack_real_pairs=pack)
+            assert torch.allclose(a, b, rtol=1e-12, atol=0.0)   # accumulation order differs between launches
+    with pytest.raises(Exception):
+        ops.wk_acf_sum(J[:, :, 5])      # series not contiguous
