@@ -175,7 +175,8 @@ template <int M1>
 __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols_tpc(const ColsTpcParams p) {
     constexpr int H = M1 / 2;
     constexpr int TPC_THREADS = TpcShape<M1>::NT;
-    constexpr int NCB = 4096 / TPC_THREADS;
+    constexpr int NCB = (4096 + TPC_THREADS - 1) / TPC_THREADS;  // the last column block may be partial
+    constexpr bool RAGGED = (4096 % TPC_THREADS) != 0;
     extern __shared__ double2 smem[];
     // thread-private zone of H double2 at zone[j * TPC_THREADS]: landing area of the two geometry streams (one
     // cp.async burst each: all H loads of a stream are in flight together, L2 latency is paid twice per
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
             // packed: A = (z, r3) of p, B = (z, r3) of q;  complex: A = (x, y), B = (z, r3) of the series' pair
             const i64 sl = packed ? (which ? 3 : 1) : (second ? 2 : 0) + which;
             const cd* src = p.Gs + item * 4 * N + sl * N + n2;
-            const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+            const int jlim = (nfr > n2 && (!RAGGED || n2 < 4096)) ? (nfr - n2 + 4095) >> 12 : 0;
             // rows j >= jlim are zero-filled (src-size 0: nothing is read; the address still lies inside the
             // workspace, whose T region follows the geometry streams)
 #pragma unroll
@@ -217,14 +218,15 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         const i64 ic = u / nslots;
         const int n2 = (int)(ic % NCB) * TPC_THREADS + threadIdx.x;
         const i64 item = ic / NCB;
-        const cd w1 = ldg_cd(p.seeds + 2 * n2), w2 = ldg_cd(p.seeds + 2 * n2 + 1);
+        const bool live = !RAGGED || n2 < 4096;   // threads past the last column run on zeros and store nothing
+        const cd w1 = ldg_cd(p.seeds + 2 * (n2 & 4095)), w2 = ldg_cd(p.seeds + 2 * (n2 & 4095) + 1);
         cd* dst = p.T + (item * nslots + slot) * TS + n2;
         // slot -> series (kernels.h): 0 Y20 p+iq | 1,2 Y21 p,q | 3,4 Y22 p,q | 5 r^-3 p+iq | 6 F20 p+iq | 7,8 F21 p,q | 9,10 F22 p,q
         const bool packed = slot == 0 || slot == 5 || slot == 6;
         const bool weighted = slot >= 6;                       // carries r^-3 (F2m)
         const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;  // (x + i y)^1 z, else (x + i y)^2
         const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
-        const int jlim = nfr > n2 ? (nfr - n2 + 4095) >> 12 : 0;
+        const int jlim = (nfr > n2 && live) ? (nfr - n2 + 4095) >> 12 : 0;
         if (p.sync_units) __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)
         cd v[H];
         if (ones) {
@@ -278,10 +280,10 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         ColCodelets<H>::even(v);
         {
             cd w = w2;
-            st_stream(dst, v[0]);
+            if (live) st_stream(dst, v[0]);
 #pragma unroll
             for (int a = 1; a < H; ++a) {
-                st_stream(dst + (i64)(2 * a) * DYNPY_T_RS, cmul(v[a], w));
+                if (live) st_stream(dst + (i64)(2 * a) * DYNPY_T_RS, cmul(v[a], w));
                 if (a + 1 < H) w = cmul(w, w2);
             }
         }
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
             cd w = w1;
 #pragma unroll
             for (int a = 0; a < H; ++a) {
-                st_stream(dst + (i64)(2 * a + 1) * DYNPY_T_RS, cmul(v[a], w));
+                if (live) st_stream(dst + (i64)(2 * a + 1) * DYNPY_T_RS, cmul(v[a], w));
                 if (a + 1 < H) w = cmul(w, w2);
             }
         }
