@@ -152,15 +152,16 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
                 if (k < 15) w = cmul(w, cs);
             }
         }
+        // next row (already on its way to L2) -> registers: issued as soon as the step-2 values have left the
+        // registers, so that the loads fly under the step-3 reads, the barrier and the last codelet;
+        // unconditional so that nx is dead during steps 1 and 2 (the last iteration re-reads its own row)
         __syncwarp();
         // ---- step 3
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = smem[pad16(tid * 16 + q)];
-        __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten
-        // next row (already on its way to L2) -> registers, under the last codelet; unconditional so that
-        // nx is dead during steps 1 and 2 (the last iteration re-reads its own row)
 #pragma unroll
         for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
+        __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten
         fft16(v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc[j]));
