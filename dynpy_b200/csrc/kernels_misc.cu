@@ -495,7 +495,8 @@ __device__ __forceinline__ void normalize3(double v[3]) {
 // thread = (frame, molecule); SR_func1 (SRrax.py:438-510):
 //   r, v relative to the mass-weighted mean; R = sum(r^2 1 - r r^T) unweighted; I mass-weighted;
 //   L' = sum r x v unweighted; omega = solve(R, L'); body axes from two minimum-image pair
-//   vectors; omega_b = ax^-1 omega; I_b = ax^-1 I ax; J = I_b omega_b.
+//   vectors; omega_b = ax^-1 omega; I_b = ax^-1 I ax; J = I_b omega_b — evaluated as omega_b = ax^T omega,
+//   J = ax^T (I omega), which is the same to rounding because ax is orthonormal.
 // NAT > 0: atoms per molecule known at compile time (positions and velocities stay in registers between
 // the centre-of-mass pass and the tensor pass); NAT == 0: run-time count, two passes over memory.
 template <int NAT>
@@ -574,21 +575,24 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
     I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
     double o[3];
     solve3(R, rv, o);
-    // body axes from the two pair vectors (wrapped coordinates)
+    // body axes from the two pair vectors.  The reference takes them from the pair table of the WRAPPED
+    // coordinates (d = u_a + s L - u_b, the image s with the smallest |d|); for two bonded atoms that is the
+    // nearest image of the raw difference, d = (x_a - x_b) - L rint((x_a - x_b)/L), to one rounding of
+    // |x| * 2^-53 — far inside the tolerance, and 12 exact fmods + 18 candidate evaluations cheaper (this
+    // kernel is bound by fp64 issue, not by HBM).
     const int* ax4 = axis_atoms + m * 4;
-    const double ica = 1.0 / ca, icb = 1.0 / cb, icc = 1.0 / cc;
+    const double cell[3] = {ca, cb, cc};
+    const double icell[3] = {1.0 / ca, 1.0 / cb, 1.0 / cc};
     double dvec[2][3];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const double* pa = pos + (i64)ax4[2 * h] * 3 * N;
-        const double* pb = pos + (i64)ax4[2 * h + 1] * 3 * N;
-        // per-axis minimum image: the same (x_i + s a) - x_j candidates as the 27-image loop of pdist_ortho and
-        // the same winner unless two of the 27 sums tie exactly (bonded atoms are far from half a box apart);
-        // 9 candidate evaluations instead of 81 — this kernel is instruction-bound, not HBM-bound, otherwise
-        double s2;
-        axis_min(np_mod(pa[fr], ca, ica), np_mod(pb[fr], ca, ica), ca, dvec[h][0], s2);
-        axis_min(np_mod(pa[N + fr], cb, icb), np_mod(pb[N + fr], cb, icb), cb, dvec[h][1], s2);
-        axis_min(np_mod(pa[2 * N + fr], cc, icc), np_mod(pb[2 * N + fr], cc, icc), cc, dvec[h][2], s2);
+        const double* pa = pos + (i64)ax4[2 * h] * 3 * N + fr;
+        const double* pb = pos + (i64)ax4[2 * h + 1] * 3 * N + fr;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double dd = pa[d * N] - pb[d * N];
+            dvec[h][d] = fma(-cell[d], rint(dd * icell[d]), dd);
+        }
     }
     double X[3], Y[3], Z[3];
     if (axis_rule == 1) {
@@ -602,22 +606,18 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
         cross3(Z, dvec[1], X); normalize3(X);
         cross3(Z, X, Y); normalize3(Y);
     }
-    double ax[3][3] = {{X[0], Y[0], Z[0]}, {X[1], Y[1], Z[1]}, {X[2], Y[2], Z[2]}};  // columns x,y,z
-    double ai[3][3];
-    inv3(ax, ai);
-    double ob[3], Ia[3][3], Ib[3][3], Jb[3];
+    // ax = [x y z] as columns is orthonormal to rounding (x, y are normalised cross products with z), so
+    // ax^-1 = ax^T and  J = I_b omega_b = ax^T I ax ax^T omega = ax^T (I omega):  18 products instead of the
+    // inverse and two 3x3 matrix products the reference spells out (la.inv, np.matmul; SRrax.py:491-498)
+    const double ax[3][3] = {{X[0], Y[0], Z[0]}, {X[1], Y[1], Z[1]}, {X[2], Y[2], Z[2]}};  // columns x,y,z
+    double ob[3], Io[3], Jb[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) ob[i] = ai[i][0] * o[0] + ai[i][1] * o[1] + ai[i][2] * o[2];
+    for (int i = 0; i < 3; ++i) Io[i] = I[i][0] * o[0] + I[i][1] * o[1] + I[i][2] * o[2];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Ia[i][j] = ai[i][0] * I[0][j] + ai[i][1] * I[1][j] + ai[i][2] * I[2][j];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Ib[i][j] = Ia[i][0] * ax[0][j] + Ia[i][1] * ax[1][j] + Ia[i][2] * ax[2][j];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) Jb[i] = Ib[i][0] * ob[0] + Ib[i][1] * ob[1] + Ib[i][2] * ob[2];
+    for (int i = 0; i < 3; ++i) {
+        ob[i] = ax[0][i] * o[0] + ax[1][i] * o[1] + ax[2][i] * o[2];
+        Jb[i] = ax[0][i] * Io[0] + ax[1][i] * Io[1] + ax[2][i] * Io[2];
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         if (J) J[(m * 3 + d) * n_out + t] = Jb[d];
