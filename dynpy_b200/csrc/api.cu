@@ -215,6 +215,7 @@ int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf
     ld.S = spectrum;
     ld.M = M;
     ld.M1 = M > DYNPY_ROW_LEN ? (int)(M / DYNPY_ROW_LEN) : 1;
+    ld.natural = 0;
     EpiParams ep;
     memset(&ep, 0, sizeof(ep));
     ep.out = acf;
@@ -234,7 +235,8 @@ int dynpy_ifft_acf_f64(const double* spectrum, int n_acc, int64_t M, double* acf
 int64_t dynpy_wk_each_workspace_bytes(int64_t M, int64_t n_series) {
     if (n_series < 1) n_series = 1;
     i64 t = M > DYNPY_ROW_LEN ? (n_series < 16 ? n_series : 16) * M * (i64)sizeof(cd) : 0;
-    return n_series * align_up(M * 8, 256) + t + 512;
+    const i64 copies = M > DYNPY_ROW_LEN ? 2 : 1;   // two-pass lengths: the spectra also in natural order
+    return copies * n_series * align_up(M * 8, 256) + t + 512;
 }
 
 int dynpy_wk_acf_each_f64(const double* re, const double* im, int64_t n_series, int64_t n, int64_t series_stride,
@@ -262,6 +264,7 @@ int dynpy_wk_acf_each_f64(const double* re, const double* im, int64_t n_series, 
     const i64 T_cap = two ? (cap < 16 ? cap : 16) : 0;
     cd* T = two ? (cd*)ws : nullptr;
     double* P = (double*)((char*)ws + align_up(T_cap * M * (i64)sizeof(cd), 256));
+    double* Pn = two ? P + cap * M : nullptr;
     const i64 pstride = align_up(M * 8, 256) / 8;
     if (pstride != M) { set_error("internal: unaligned spectrum stride"); return DYNPY_ERR_INVALID; }
     for (i64 s0 = 0; s0 < n_series; s0 += cap) {
@@ -285,6 +288,12 @@ int dynpy_wk_acf_each_f64(const double* re, const double* im, int64_t n_series, 
         sl.S = P;
         sl.M = M;
         sl.M1 = two ? (int)(M / DYNPY_ROW_LEN) : 1;
+        sl.natural = 0;
+        if (two) {
+            DYNPY_CHECK(launch_spectrum_to_natural(P, Pn, cnt, sl.M1, st), "wk each transpose");
+            sl.S = Pn;
+            sl.natural = 1;
+        }
         EpiParams e2;
         memset(&e2, 0, sizeof(e2));
         e2.out = acf + s0 * n;
@@ -543,7 +552,7 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
 static i64 dd_ragged_pair_bytes(i64 N, i64 M) {
     i64 w = align_up(14 * N * 8, 256);        // compressed words
     i64 fi = align_up(N * 4, 256);            // rank -> frame
-    i64 p = align_up(7 * M * 8, 256);         // per-series power spectra
+    i64 p = align_up(7 * M * 8, 256) * (M > DYNPY_ROW_LEN ? 2 : 1);  // per-series power spectra (+ natural-order copy)
     i64 acf = align_up(7 * N * 8, 256);       // per-series ACFs
     i64 small = 7 * 8 * 2 + 16 + 256;         // lens, scale, bias
     return w + fi + p + acf + small;
@@ -596,6 +605,7 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
     int* fidx = (int*)carve(cap * N * 4);
     double* W = (double*)carve(cap * 14 * N * 8);
     double* P = (double*)carve(cap * 7 * M * 8);
+    double* Pn = M > DYNPY_ROW_LEN ? (double*)carve(cap * 7 * M * 8) : nullptr;
     double* acf = (double*)carve(cap * 7 * N * 8);
     cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
     const i64 T_cap = tbytes ? 14 : 0;
@@ -628,6 +638,12 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
         sl.S = P;
         sl.M = M;
         sl.M1 = M > DYNPY_ROW_LEN ? (int)(M / DYNPY_ROW_LEN) : 1;
+        sl.natural = 0;
+        if (Pn) {
+            DYNPY_CHECK(launch_spectrum_to_natural(P, Pn, cnt * 7, sl.M1, st), "dd ragged transpose");
+            sl.S = Pn;
+            sl.natural = 1;
+        }
         EpiParams e2;
         memset(&e2, 0, sizeof(e2));
         e2.out = acf;

@@ -277,10 +277,13 @@ struct SpectrumLoader {
     const double* S;
     i64 M;
     int M1;  // 1 for single-pass spectra
+    int natural;  // 1: S is in natural frequency order (after k_spectrum_to_natural); 0: the engine's internal order
     struct Ctx { const double* s; };
     __device__ __forceinline__ Ctx begin(i64 f) const { Ctx c; c.s = S + f * M; return c; }
     __device__ __forceinline__ cd load(const Ctx& c, i64 n) const {
-        i64 idx = (M1 > 1) ? (n % M1) * (i64)DYNPY_ROW_LEN + n / M1 : n;
+        // internal order: element n sits at [n % M1][n / M1] — consecutive columns of the inverse's column pass hit
+        // different 32-byte sectors (a gather); spectra that are transformed back one by one are transposed first
+        i64 idx = (M1 > 1 && !natural) ? (n % M1) * (i64)DYNPY_ROW_LEN + n / M1 : n;
         return make_double2(__ldg(c.s + idx), 0.0);
     }
     __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const { return load(c, n); }

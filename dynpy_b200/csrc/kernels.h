@@ -38,6 +38,7 @@ cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i
 cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const int* mol_atoms, i64 n_mol, int nat,
                              const double* mass, const int* axis_atoms, int axis_rule, double a, double b, double c,
                              double inv_dt, double* J, double* omega, double* axes, cudaStream_t st);
+cudaError_t launch_spectrum_to_natural(const double* in, double* out, i64 n_spec, int M1, cudaStream_t st);
 cudaError_t launch_simpson(const double* y, const double* x, i64 n, int n_cols, i64 col_stride, int mode,
                            double* out, cudaStream_t st);
 

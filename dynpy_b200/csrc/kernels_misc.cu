@@ -436,6 +436,38 @@ cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i
     return cudaGetLastError();
 }
 
+// Power spectra from the engine's internal order [f][k1][k2] (k = k1 + M1 k2) to natural order [f][k2][k1]:
+// a tiled transpose, both sides coalesced.  The column pass of an inverse transform then reads its input
+// with unit stride instead of gathering one 8-byte element per 32-byte sector.
+__global__ void __launch_bounds__(256) k_spectrum_to_natural(const double* __restrict__ in, double* __restrict__ out,
+                                                             int M1) {
+    __shared__ double tile[32][33];
+    const i64 f = blockIdx.z;
+    in += f * (i64)M1 * DYNPY_ROW_LEN;
+    out += f * (i64)M1 * DYNPY_ROW_LEN;
+    const int k2_0 = blockIdx.x * 32, k1_0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + j;
+        if (k1 < M1) tile[j][tx] = in[(i64)k1 * DYNPY_ROW_LEN + k2_0 + tx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + tx;
+        if (k1 < M1) out[(i64)(k2_0 + j) * M1 + k1] = tile[tx][j];
+    }
+}
+cudaError_t launch_spectrum_to_natural(const double* in, double* out, i64 n_spec, int M1, cudaStream_t st) {
+    for (i64 f0 = 0; f0 < n_spec; f0 += 32768) {
+        const i64 cnt = n_spec - f0 < 32768 ? n_spec - f0 : 32768;
+        dim3 grid(DYNPY_ROW_LEN / 32, (unsigned)((M1 + 31) / 32), (unsigned)cnt);
+        k_spectrum_to_natural<<<grid, 256, 0, st>>>(in + f0 * (i64)M1 * DYNPY_ROW_LEN, out + f0 * (i64)M1 * DYNPY_ROW_LEN, M1);
+    }
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ spin-rotation
 __device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3], double x[3]) {
     // Gaussian elimination with partial pivoting (what numpy.linalg.solve / LAPACK gesv does)

@@ -309,7 +309,7 @@ def dd_pairs_to_spectrum(coords, pair_i, pair_j, cell, M=None, spectrum=None, ws
     return spectrum
 
 
-def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 2 << 30, mask=None,
+def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 8 << 30, mask=None,
                            pair_frames=None, frame_hit=None):
     """Ragged dipolar path: G[7, F] += per-pair ACFs binned at the k-th present frame.  Optional mask [P, F]
     uint8 (frames in which the pair row passes the molecule filter), pair_frames [P] int64 out (frames present),
