@@ -327,8 +327,11 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
                   i64 pair0, double a, double b, double c, double rmax2, double* __restrict__ W,
                   int* __restrict__ fidx, i64* __restrict__ lens, double* __restrict__ scale,
                   double* __restrict__ bias, const unsigned char* __restrict__ mask) {
-    __shared__ int wcnt[8];
-    __shared__ i64 base;
+    // E sub-rows of 256 frames per round and ONE barrier per round (the per-warp counts are double-buffered and
+    // every thread carries the running output position itself): the kernel is bound by load latency and
+    // barriers, not by bandwidth
+    constexpr int E = 4;
+    __shared__ int wcnt[2][E][8];
     __shared__ double sh[8];
     const i64 pl = blockIdx.x;
     const i64 p = pair0 + pl;
@@ -336,43 +339,62 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
     const double* xj = X + (i64)pj[p] * 3 * N;
     double* w = W + pl * 14 * N;
     int* fi = fidx + pl * N;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
     double rsum = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (i64 n0 = 0; n0 < N; n0 += 256) {
-        const i64 n = n0 + threadIdx.x;
-        bool ok = false;
-        DDWords d;
-        if (n < N) {
-            double dx, dy, dz, sx, sy, sz;
-            axis_min(__ldg(xi + n), __ldg(xj + n), a, dx, sx);
-            axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, dy, sy);
-            axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, dz, sz);
-            const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
-            ok = r2 < rmax2 && (!mask || mask[p * N + n]);  // mask: frames in which the pair row passes the molecule filter
-            if (ok) d = dd_words(dx, dy, dz, r2);
+    const unsigned below = (1u << lane) - 1u;
+    i64 base = 0;
+    int buf = 0;
+    for (i64 n0 = 0; n0 < N; n0 += 256 * E, buf ^= 1) {
+        double dx[E], dy[E], dz[E], r2[E];
+        unsigned ball[E];
+        bool ok[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const i64 n = n0 + e * 256 + threadIdx.x;
+            ok[e] = false;
+            dx[e] = dy[e] = dz[e] = 0.0;
+            r2[e] = 1.0;
+            if (n < N) {
+                double sx, sy, sz;
+                axis_min(__ldg(xi + n), __ldg(xj + n), a, dx[e], sx);
+                axis_min(__ldg(xi + N + n), __ldg(xj + N + n), b, dy[e], sy);
+                axis_min(__ldg(xi + 2 * N + n), __ldg(xj + 2 * N + n), c, dz[e], sz);
+                r2[e] = __dadd_rn(__dadd_rn(sx, sy), sz);
+                ok[e] = r2[e] < rmax2 && (!mask || mask[p * N + n]);  // mask: frames in which the pair row passes the molecule filter
+            }
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) wcnt[warp] = __popc(ball);
-        __syncthreads();
-        if (ok) {
-            i64 off = base;
-            for (int q = 0; q < warp; ++q) off += wcnt[q];
-            off += __popc(ball & ((1u << lane) - 1u));
-            fi[off] = (int)n;
-            w[0 * N + off] = d.y20;  w[1 * N + off] = 0.0;
-            w[2 * N + off] = d.y21r; w[3 * N + off] = d.y21i;
-            w[4 * N + off] = d.y22r; w[5 * N + off] = d.y22i;
-            w[6 * N + off] = d.r3;   w[7 * N + off] = 0.0;
-            w[8 * N + off] = d.f20;  w[9 * N + off] = 0.0;
-            w[10 * N + off] = d.f21r; w[11 * N + off] = d.f21i;
-            w[12 * N + off] = d.f22r; w[13 * N + off] = d.f22i;
-            rsum += d.r3;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ball[e] = __ballot_sync(0xffffffffu, ok[e]);
+            if (lane == 0) wcnt[buf][e][warp] = __popc(ball[e]);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += wcnt[q]; base += t; }
-        __syncthreads();
+        i64 off = base;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int mine = 0, tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int cq = wcnt[buf][e][q];
+                tot += cq;
+                if (q < warp) mine += cq;
+            }
+            if (ok[e]) {
+                const i64 o = off + mine + __popc(ball[e] & below);
+                const DDWords d = dd_words(dx[e], dy[e], dz[e], r2[e]);
+                fi[o] = (int)(n0 + e * 256 + threadIdx.x);
+                w[0 * N + o] = d.y20;  w[1 * N + o] = 0.0;
+                w[2 * N + o] = d.y21r; w[3 * N + o] = d.y21i;
+                w[4 * N + o] = d.y22r; w[5 * N + o] = d.y22i;
+                w[6 * N + o] = d.r3;   w[7 * N + o] = 0.0;
+                w[8 * N + o] = d.f20;  w[9 * N + o] = 0.0;
+                w[10 * N + o] = d.f21r; w[11 * N + o] = d.f21i;
+                w[12 * N + o] = d.f22r; w[13 * N + o] = d.f22i;
+                rsum += d.r3;
+            }
+            off += tot;
+        }
+        base = off;
     }
     const double t = block_sum_256(rsum, sh);
     if (threadIdx.x == 0) {
