@@ -12,7 +12,8 @@ static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
 
 bool dd2_supported(i64 M) {
     const i64 m1 = M >> 12;
-    return (M & 4095) == 0 && (m1 == 16 || m1 == 20 || m1 == 24 || m1 == 32 || m1 == 40 || m1 == 50 || m1 == 64);
+    return (M & 4095) == 0 && (m1 == 16 || m1 == 20 || m1 == 24 || m1 == 32 || m1 == 40 || m1 == 50 || m1 == 64 ||
+                               m1 == 512);
 }
 
 // bytes of one padded transform of T
@@ -23,6 +24,25 @@ i64 dd2_workspace_bytes(i64 M, i64 N, i64 items) {
     if (items < 1) items = 1;
     return t_bytes(M) + M * (i64)sizeof(cd) + align_up2(items * 16, 256) + align_up2(items * 64 * N, 256) +
            items * DD_NSLOTS * t_bytes(M) + 1024;
+}
+
+// long columns (M1 = 512): two-level thread-per-column kernel, C columns per CTA
+#ifndef TPC2_C
+#define TPC2_C 8
+#endif
+static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
+    ProfScope prof(PROF_COLS, st);
+    constexpr int B = 32, C = TPC2_C;
+    const size_t smem = (size_t)16 * B * C * sizeof(cd);
+    cudaError_t e = cudaFuncSetAttribute(k_cols_tpc2<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int tiles = 4096 / C;
+    const int per_sm = 512 / (B * C);
+    int gy = (4 * per_sm * n_sm + tiles - 1) / tiles;   // >= 4 waves
+    if (gy > p.items) gy = (int)p.items;
+    if (gy < 1) gy = 1;
+    k_cols_tpc2<B, C><<<dim3(tiles, gy), B * C, smem, st>>>(p, tw);
+    return cudaGetLastError();
 }
 
 template <int M1>
@@ -84,7 +104,7 @@ static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStre
     k_cols_tpc<M1><<<per_sm * n_sm, TPC_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
-static cudaError_t launch_cols_tpc(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
+static cudaError_t launch_cols_tpc(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
     switch ((int)(p.M >> 12)) {
         case 16: return launch_cols_tpc_M1<16>(p, n_sm, st);
         case 32: return launch_cols_tpc_M1<32>(p, n_sm, st);
@@ -93,6 +113,7 @@ static cudaError_t launch_cols_tpc(const ColsTpcParams& p, int n_sm, cudaStream_
         case 20: return launch_cols_tpc_M1<20>(p, n_sm, st);
         case 24: return launch_cols_tpc_M1<24>(p, n_sm, st);
         case 40: return launch_cols_tpc_M1<40>(p, n_sm, st);
+        case 512: return launch_cols_tpc2(p, tw, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -173,7 +194,7 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
             tp.items = cnt;
             tp.pair0 = 2 * it0;
             tp.n_pairs = P;
-            DYNPY_CHECK(launch_cols_tpc(tp, n_sm, st), "dd columns");
+            DYNPY_CHECK(launch_cols_tpc(tp, tw, n_sm, st), "dd columns");
         } else {
             cp.pair0 = 2 * it0;
             cp.items = cnt;

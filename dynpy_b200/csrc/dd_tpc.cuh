@@ -303,4 +303,129 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
     }
 }
 
+// ---------------------------------------------------------------- long columns: M1 = 16 B (B = 16, 32)
+// Two-level form of the same idea for the column lengths of long trajectories (M1 = 512 for 1e6 frames).
+// n1 = B a + b (a < 16, only a < 8 is non-zero: the series fills at most half of M), k1 = c + 16 d:
+//   X[c + 16 d] = sum_b W_B^{b d} W_M1^{b c} sum_a x[B a + b] W_16^{a c}.
+// Phase A, thread (b, column): the 8 samples of its residue b are formed from the geometry streams, the pruned
+//   16-point transform over a is the fft8 / fft8_odd pair, the result times W_M1^{b c} goes to shared memory.
+// Phase C, thread (c, parity, column): the B-point transform over b as a radix-2 split in registers
+//   (fft_{B/2} of y[b] + y[b + B/2], fft_{B/2}_odd of the difference), inter-pass twiddle chain, 128-byte stores.
+// A CTA keeps its tile of C columns (B C threads) and walks through the series of its items, so the twiddle
+// seeds are loop-invariant and the geometry tile it re-reads for the 11 series of an item stays in L2.
+template <int B> struct Tpc2Codelets;
+template <> struct Tpc2Codelets<32> {
+    static __device__ __forceinline__ void even(cd (&v)[16]) { fft16(v); }
+    static __device__ __forceinline__ void odd(cd (&v)[16]) { fft16_odd(v); }
+};
+
+template <int B, int C>
+__global__ void __launch_bounds__(B * C, 512 / (B * C)) k_cols_tpc2(const ColsTpcParams p, const cd* __restrict__ twp) {
+    static_assert(B == 32, "phase A (B x C threads) and phase C (16 x 2 x C threads) use the same threads only for B = 32");
+    constexpr int M1 = 16 * B;       // C = columns per CTA (B * C threads)
+    constexpr int HB = B / 2;
+    extern __shared__ double2 smem[];  // S[c][b][col], 16 * B * C entries
+    const int tid = threadIdx.x;
+    const i64 N = p.N;
+    const int nfr = (int)(N < (i64)(M1 / 2) * 4096 ? N : (i64)(M1 / 2) * 4096);
+    const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
+    const double KF = 1.5853309190424043;
+    constexpr i64 TS = (i64)M1 * DYNPY_T_RS;
+    const int tile = blockIdx.x;
+    // phase A role
+    const int colA = tid % C, bA = tid / C;
+    const int n2A = tile * C + colA;
+    const cd tb = ldg_cd(twp + bA * (4096 / M1));       // W_M1^b
+    // phase C role
+    const int colC = tid % C, par = (tid / C) & 1, cC = tid / (2 * C);
+    const int n2C = tile * C + colC;
+    const double inv_M = 1.0 / (double)p.M;
+    const cd seed = w_exact(((i64)n2C * (cC + 16 * par)) % p.M, inv_M);   // W_M^{n2 (c + 16 p)}
+    const cd step = w_exact(((i64)n2C * 32) % p.M, inv_M);                // W_M^{32 n2}
+
+    for (i64 item = blockIdx.y; item < p.items; item += gridDim.y) {
+        const cd* g = p.Gs + item * 4 * N;
+        const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
+        for (int slot = 0; slot < 11; ++slot) {
+            const bool packed = slot == 0 || slot == 5 || slot == 6;
+            const bool second = slot == 2 || slot == 4 || slot == 8 || slot == 10;
+            const bool weighted = slot >= 6;
+            const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;
+            // ---- phase A: samples n1 = B a + b, a = 0..7
+            cd v[8];
+            {
+                const cd* sa = g + (packed ? 1 : (second ? 2 : 0)) * N;   // packed: (z, r3) of p ; complex: (x, y)
+                const cd* sb = g + (packed ? 3 : (second ? 3 : 1)) * N;   // packed: (z, r3) of q ; complex: (z, r3)
+                cd ra[8], rb[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
+                    const bool on = fr < nfr;
+                    ra[a] = on ? ldg_cd(sa + fr) : make_double2(0.0, 0.0);
+                    rb[a] = on ? ldg_cd(sb + fr) : make_double2(0.0, 0.0);
+                }
+                if (packed) {
+                    const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
+                    const double mp = slot == 5 ? __ldg(p.rsum + 2 * item) * p.inv_n : 0.0;
+                    const double mq = slot == 5 ? __ldg(p.rsum + 2 * item + 1) * p.inv_n : 0.0;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const bool on = (i64)(B * a + bA) * 4096 + n2A < nfr;
+                        const double yp = slot == 5 ? 1.0 : fma(3.0 * ra[a].x, ra[a].x, -1.0);
+                        const double yq = slot == 5 ? 1.0 : fma(3.0 * rb[a].x, rb[a].x, -1.0);
+                        v[a].x = on ? (slot == 0 ? c : c * ra[a].y) * yp - mp : 0.0;
+                        v[a].y = (on && q_exists) ? (slot == 0 ? c : c * rb[a].y) * yq - mq : 0.0;
+                    }
+                } else {
+                    const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const cd xy = ra[a], zr = rb[a];
+                        const cd w = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                        const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
+                        v[a] = make_double2(sc * w.x, sc * w.y);
+                    }
+                }
+            }
+            {
+                cd e[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) e[a] = v[a];
+                fft8(e);        // y[2 c']
+                fft8_odd(v);    // y[2 c' + 1]
+                // times W_M1^{b c}: chain over c
+                cd w = tb;      // c = 1
+                smem[(0 * B + bA) * C + colA] = e[0];
+#pragma unroll
+                for (int c = 1; c < 16; ++c) {
+                    const cd y = (c & 1) ? v[c >> 1] : e[c >> 1];
+                    smem[(c * B + bA) * C + colA] = cmul(y, w);
+                    if (c < 15) w = cmul(w, tb);
+                }
+            }
+            __syncthreads();
+            // ---- phase C: B-point transform over b for (c, column), parity `par`
+            cd u[HB];
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const cd y0 = smem[(cC * B + j) * C + colC];
+                const cd y1 = smem[(cC * B + j + HB) * C + colC];
+                u[j] = par ? make_double2(y0.x - y1.x, y0.y - y1.y) : make_double2(y0.x + y1.x, y0.y + y1.y);
+            }
+            __syncthreads();   // the buffer may be rewritten by the next series
+            if (par) Tpc2Codelets<B>::odd(u); else Tpc2Codelets<B>::even(u);
+            cd* dst = p.T + (item * 11 + slot) * TS + n2C;
+            {
+                cd w = seed;
+#pragma unroll
+                for (int dd = 0; dd < HB; ++dd) {
+                    const int k1 = cC + 16 * (2 * dd + par);
+                    st_stream(dst + (i64)k1 * DYNPY_T_RS, cmul(u[dd], w));
+                    if (dd + 1 < HB) w = cmul(w, step);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace dynpy

@@ -235,16 +235,17 @@ def test_dd_fast_path_vs_oracle(ops, F, P, budget_mb):
         assert np.max(np.abs(G[c] - ref[c])) / denom < 1e-10, (c, np.max(np.abs(G[c] - ref[c])) / denom)
 
 
-def test_dd_fast_path_matches_generic_engine(ops, monkeypatch):
+@pytest.mark.parametrize("F,P", [(100000, 301), (600000, 23)])
+def test_dd_fast_path_matches_generic_engine(ops, monkeypatch, F, P):
     """DYNPY_DD_PATH=v1 routes the same call through the generic word generator + engine: both paths
-    must agree to rounding on a workload large enough for many batches and work ranges."""
+    must agree to rounding on a workload large enough for many batches and work ranges (1e5 frames: the
+    thread-per-column kernel, M1 = 50; 6e5 frames: the two-level kernel for 512-point columns, M = 2^21)."""
     from dynpy_b200 import synth
-    F = 100000
     box = synth.water_box(16, seed=3).to("cuda")
     hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
-    w = ops.wrap(box.trajectory(F, chunk=4096, atom_mask=hidx), box.celldm)
+    w = ops.wrap(box.trajectory(F, chunk=1 << 15, atom_mask=hidx), box.celldm)
     i, j = np.triu_indices(32, k=1)
-    pi, pj = dev(i[:301], torch.int32), dev(j[:301], torch.int32)
+    pi, pj = dev(i[:P], torch.int32), dev(j[:P], torch.int32)
     L = box.celldm
     out = {}
     for path in ("v1", "v2"):
