@@ -28,7 +28,7 @@ i64 dd2_workspace_bytes(i64 M, i64 N, i64 items) {
 
 // long columns (M1 = 512): two-level thread-per-column kernel, C columns per CTA
 #ifndef TPC2_C
-#define TPC2_C 8
+#define TPC2_C 4
 #endif
 static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);
@@ -37,7 +37,7 @@ static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_
     cudaError_t e = cudaFuncSetAttribute(k_cols_tpc2<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int tiles = 4096 / C;
-    const int per_sm = 512 / (B * C);
+    const int per_sm = 384 / (B * C);
     int gy = (4 * per_sm * n_sm + tiles - 1) / tiles;   // >= 4 waves
     if (gy > p.items) gy = (int)p.items;
     if (gy < 1) gy = 1;

@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
 //   16-point transform over a is the fft8 / fft8_odd pair, the result times W_M1^{b c} goes to shared memory.
 // Phase C, thread (c, parity, column): the B-point transform over b as a radix-2 split in registers
 //   (fft_{B/2} of y[b] + y[b + B/2], fft_{B/2}_odd of the difference), inter-pass twiddle chain, 128-byte stores.
+// 384 threads per SM (3 CTAs of 4 columns: 168 registers, 68 B of spills) beat 512 at 128 registers.
 // A CTA keeps its tile of C columns (B C threads) and walks through the series of its items, so the twiddle
 // seeds are loop-invariant and the geometry tile it re-reads for the 11 series of an item stays in L2.
 template <int B> struct Tpc2Codelets;
@@ -320,7 +321,7 @@ template <> struct Tpc2Codelets<32> {
 };
 
 template <int B, int C>
-__global__ void __launch_bounds__(B * C, 512 / (B * C)) k_cols_tpc2(const ColsTpcParams p, const cd* __restrict__ twp) {
+__global__ void __launch_bounds__(B * C, 384 / (B * C)) k_cols_tpc2(const ColsTpcParams p, const cd* __restrict__ twp) {
     static_assert(B == 32, "phase A (B x C threads) and phase C (16 x 2 x C threads) use the same threads only for B = 32");
     constexpr int M1 = 16 * B;       // C = columns per CTA (B * C threads)
     constexpr int HB = B / 2;
