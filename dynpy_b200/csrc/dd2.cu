@@ -120,13 +120,13 @@ static cudaError_t launch_cols_tpc(const ColsTpcParams& p, const cd* tw, int n_s
 
 int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double a, double b, double c, double* S,
             i64 M, void* ws, i64 ws_bytes, const cd* tw, int n_sm, cudaStream_t st) {
-    // column kernel: thread-per-column (dd_tpc.cuh) except for M1 = 64, whose 32-point in-register halves
-    // do not fit 168 registers without spilling (there the warp-exchange kernel of dd_cols2.cuh is faster);
-    // DYNPY_DD_COLS=warp|tpc overrides (A/B checks)
+    // column kernel: thread-per-column (dd_tpc.cuh); DYNPY_DD_COLS=warp selects the warp-exchange kernel of
+    // dd_cols2.cuh where it exists (M1 = 32, 64; A/B checks — it was the faster one for M1 = 64 until the
+    // thread-per-column kernel got 255 registers there)
     const char* sel = getenv("DYNPY_DD_COLS");
     const i64 m1 = M >> 12;
     const bool warp_ok = m1 == 32 || m1 == 64;
-    const bool tpc = sel ? (sel[0] != 'w' || !warp_ok) : m1 != 64;
+    const bool tpc = sel ? (sel[0] != 'w' || !warp_ok) : true;
     const i64 items_all = (P + 1) / 2;
     const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 1024;
     const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16 + 64 * N;

@@ -119,14 +119,20 @@ __device__ __forceinline__ void st_stream(cd* p, cd v) {
 
 // threads per CTA of the column kernel: 256 x 2 CTAs per SM (8 warps running the same straight-line code
 // close together keep the instruction caches effective: 128 x 4 lost 12 %; two independent CTAs overlap
-// their load and compute phases: 512 x 1 lost 5 %); 128 x 3 CTAs for M1 = 64, whose 32-point halves need
-// 168 registers
+// their load and compute phases: 512 x 1 lost 5 %; 128 x 2-3 or 256 x 1 at 168-255 registers: 8 % slower for
+// M1 = 50); 128 x 2 CTAs at 255 registers for M1 = 64, whose 32-point halves spill at anything less
 #ifndef TPC_NT
 #define TPC_NT 256
 #endif
+#ifndef TPC_PER_SM
+#define TPC_PER_SM (512 / TPC_NT)
+#endif
+#ifndef TPC64_PER_SM
+#define TPC64_PER_SM 2   // M1 = 64: 32-point halves need ~250 registers; 2 x 128 threads without spills beat 3 x 128 with
+#endif
 template <int M1> struct TpcShape {
     static constexpr int NT = M1 >= 64 ? 128 : TPC_NT;
-    static constexpr int PER_SM = M1 >= 64 ? 3 : 512 / TPC_NT;
+    static constexpr int PER_SM = M1 >= 64 ? TPC64_PER_SM : TPC_PER_SM;
 };
 
 template <int H> struct ColCodelets;
