@@ -3,6 +3,7 @@ prep_DD_uni1 :133-169) on top of the CUDA path.  Same parameter classes, prompts
 result lines and CSV files (``<traj_dir><traj>/avg-acf.csv``, ``<traj_dir>DD-results.csv``)."""
 from __future__ import annotations
 
+import sys
 import time
 
 import numpy as np
@@ -107,23 +108,40 @@ def DD_module_main(PD, DD):
         pair_type = 'all'
     simpson_mode = getattr(DD, 'simpson_mode', None) or default_simpson_mode()
     rank, world = dist.rank_world()
+    # rank 0 asks; its decision (and the trajectory list it may have filled in) goes to every rank, so that
+    # an "n" stops the whole job instead of leaving the other ranks in a barrier
+    decision = None
     if rank == 0:
-        which_trajs(PD)
-    dist.barrier()
+        try:
+            which_trajs(PD)
+            decision = ("go", list(PD.trajs))
+        except SystemExit as e:
+            decision = ("exit", e.code)
+        except EOFError:
+            decision = ("eof", None)
+    decision = dist.broadcast_object(decision)
+    if decision[0] == "exit":
+        dist.shutdown()
+        sys.exit(decision[1])
+    if decision[0] == "eof":
+        dist.shutdown()
+        raise EOFError("EOF when reading a line")
+    PD.trajs = decision[1]
+    say = print if rank == 0 else (lambda *a, **k: None)   # user-facing lines once, not once per rank
     res = {}
     for t, traj in enumerate(PD.trajs):
         inner_start_time = time.time()
         tr = parseMD.PARSE_MD(PD, traj)
-        print("computing two-atom distances...")
-        print("computing dipolar quantities...")
-        print("computing TCFs...")
+        say("computing two-atom distances...")
+        say("computing dipolar quantities...")
+        say("computing TCFs...")
         acf_avg, rax, tc, F, info = dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson_mode)
         torch.cuda.synchronize()
-        print("--- {t:.2f} seconds ---".format(t=time.time() - inner_start_time))
+        say("--- {t:.2f} seconds ---".format(t=time.time() - inner_start_time))
         if rank == 0:
             acf_avg.to_csv(PD.traj_dir + traj + '/avg-acf.csv')
-        print("1/T1/nH = {r:.3e} Hz, tau_c = {t:.3e} ps, <F(0)^2> = {f:.3e} au^-6".format(r=rax, t=tc, f=F))
-        print("For intramolecular contrib. in heteronuclear systems (e.g. C--H relaxation of 13C), multiply 1/T1/nH "
+        say("1/T1/nH = {r:.3e} Hz, tau_c = {t:.3e} ps, <F(0)^2> = {f:.3e} au^-6".format(r=rax, t=tc, f=F))
+        say("For intramolecular contrib. in heteronuclear systems (e.g. C--H relaxation of 13C), multiply 1/T1/nH "
               "by number of bonded spins to obtain 1/T1. E.g. for C-13 in methyl group, nH=3")
         res[traj] = [rax, tc, F]
     res_df = pd.DataFrame(res).T

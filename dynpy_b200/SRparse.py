@@ -119,6 +119,13 @@ def sr_trajectory(tr, PD, SR, simpson_mode, per_molecule_acfs=True):
             use = [atoms[k] for k in sorted(methyl_indeces)]
         mol_atoms.append(use)
         axis_atoms.append(ax4)
+    # one per-slot mass vector serves every molecule: the element order inside each kept molecule (ascending
+    # atom label) must therefore be the same; the reference maps the mass per atom row (SRrax.py:448-451)
+    sym0 = [tr.symbols[a] for a in mol_atoms[0]]
+    for use in mol_atoms[1:]:
+        if [tr.symbols[a] for a in use] != sym0:
+            raise ValueError("molecules of type %r list their elements in different orders (%s vs %s): "
+                             "per-slot masses would be wrong" % (SR.mol_type, sym0, [tr.symbols[a] for a in use]))
     mass = torch.tensor(topo.masses(mol_atoms[0]), dtype=torch.float64, device=dev)
     J, om, ax = ops.sr_angmom(tr.pos, torch.tensor(mol_atoms, dtype=torch.int32, device=dev), mass,
                               torch.tensor(axis_atoms, dtype=torch.int32, device=dev), rule, cell, inv_dt, vel=tr.vel)
@@ -186,6 +193,7 @@ def SR_module_main(PD, SR):
     outer_start_time = time.time()
     simpson_mode = getattr(SR, 'simpson_mode', None) or default_simpson_mode()
     rank, world = dist.rank_world()
+    say = print if rank == 0 else (lambda *a, **k: None)   # user-facing lines once, not once per rank
     res = {}
     for t, traj in enumerate(PD.trajs):
         inner_start_time = time.time()
@@ -198,13 +206,13 @@ def SR_module_main(PD, SR):
                 tabs[name].to_csv(PD.traj_dir + traj + '/' + name + '.csv')
         tx, ty, tz = out["tau"]
         r = out["rate"]
-        print("1/T1     =     {t:.4f} Hz".format(t=r))
-        print("Total SR Run Time for {s}    --- {t:.2f} seconds ---".format(s=PD.traj_dir + traj,
+        say("1/T1     =     {t:.4f} Hz".format(t=r))
+        say("Total SR Run Time for {s}    --- {t:.2f} seconds ---".format(s=PD.traj_dir + traj,
                                                                             t=time.time() - inner_start_time))
         res[traj] = tx, ty, tz, r
     res_df = pd.DataFrame(res).T
     res_df.columns = ["tau_x", "tau_y", "tau_z", "1/T1"]
     if rank == 0:
         res_df.to_csv(PD.traj_dir + 'SR-results.csv')
-    print("Total SR Run Time         --- {t:.2f} seconds ---".format(t=time.time() - outer_start_time))
+    say("Total SR Run Time         --- {t:.2f} seconds ---".format(t=time.time() - outer_start_time))
     return res_df

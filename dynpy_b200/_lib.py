@@ -50,6 +50,7 @@ SIGNATURES = {
     "dynpy_dft_f64": (i32, [p, p, i64, i64, p, i64, p, i64, p]),
     "dynpy_cutoff_bounds_f64": (i32, [p, i64, i32, i64, i32, f64, p, p]),
     "dynpy_parse_md_blocks_host": (i32, [C.c_char_p, i64, i32, i32, p, i64, f64, p, p, i32]),
+    "dynpy_parse_md_blocks_hdr_host": (i32, [C.c_char_p, i64, i32, i32, p, i64, f64, p, p, p, i32]),
 }
 
 

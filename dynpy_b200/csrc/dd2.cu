@@ -130,7 +130,10 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     const i64 items_all = (P + 1) / 2;
     const i64 fixed = t_bytes(M) + M * (i64)sizeof(cd) + 1024;
     const i64 per_item = (i64)DD_NSLOTS * t_bytes(M) + 16 + 64 * N;
-    i64 cap = (ws_bytes - fixed - 512) / per_item;
+    // the largest batch whose carving (same formula as dd2_workspace_bytes) fits the caller's workspace
+    i64 cap = (ws_bytes - fixed) / per_item;
+    if (cap > items_all) cap = items_all;
+    while (cap >= 1 && dd2_workspace_bytes(M, N, cap) > ws_bytes) --cap;
     if (cap < 1) {
         set_error("dipolar fast path: workspace too small (need >= %lld bytes)", (long long)dd2_workspace_bytes(M, N, 1));
         return DYNPY_ERR_WORKSPACE;

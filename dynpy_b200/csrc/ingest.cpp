@@ -65,11 +65,32 @@ inline bool parse_double(const char* s, const char* t, double& v) {
 extern "C" {
 #pragma GCC visibility push(default)
 
+static int parse_blocks(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
+                        const int64_t* printed_host, int64_t n_printed, double scale_div, double* out_host,
+                        char* symbols_host, double* header_first_host, int32_t n_threads);
+
 int dynpy_parse_md_blocks_host(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
                                const int64_t* printed_host, int64_t n_printed, double scale_div, double* out_host,
                                char* symbols_host, int32_t n_threads) {
-    if (!path || nat < 1 || header_lines < 0 || first_col < 0 || !printed_host || n_printed < 1 || !out_host ||
-        !(scale_div > 0.0)) {
+    return parse_blocks(path, nat, header_lines, first_col, printed_host, n_printed, scale_div, out_host, symbols_host,
+                        nullptr, n_threads);
+}
+
+int dynpy_parse_md_blocks_hdr_host(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
+                                   const int64_t* printed_host, int64_t n_printed, double scale_div, double* out_host,
+                                   char* symbols_host, double* header_first_host, int32_t n_threads) {
+    return parse_blocks(path, nat, header_lines, first_col, printed_host, n_printed, scale_div, out_host, symbols_host,
+                        header_first_host, n_threads);
+}
+
+// first_col = index of the symbol token (the coordinates are the three tokens after it), or -1 for lines that are
+// "x y z" only (QE .pos); header_first_host (optional, needs header_lines >= 1): first token of each selected
+// block's first header line as a number (the step id of a QE .pos / .vel header)
+static int parse_blocks(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
+                        const int64_t* printed_host, int64_t n_printed, double scale_div, double* out_host,
+                        char* symbols_host, double* header_first_host, int32_t n_threads) {
+    if (!path || nat < 1 || header_lines < 0 || first_col < -1 || !printed_host || n_printed < 1 || !out_host ||
+        !(scale_div > 0.0) || (header_first_host && header_lines < 1)) {
         dynpy::set_error("dynpy_parse_md_blocks_host: invalid arguments");
         return DYNPY_ERR_INVALID;
     }
@@ -172,17 +193,34 @@ int dynpy_parse_md_blocks_host(const char* path, int64_t nat, int32_t header_lin
     };
     auto parse = [&]() {
         for (int64_t k; (k = nextf.fetch_add(1)) < n_printed && !bad.load();) {
-            const char* s = line_start((printed_host[k] - 1) * blk + header_lines);
+            const char* s = line_start((printed_host[k] - 1) * blk);
             if (!s) { fail("internal: line index out of range"); return; }
+            if (header_first_host) {
+                const char* le = (const char*)memchr(s, '\n', (size_t)(end - s));
+                if (!le) le = end;
+                const char* c = skip_ws(s, le);
+                const char* t = skip_tok(c, le);
+                double v;
+                if (t == c || !parse_double(c, t, v)) {
+                    fail("frame " + std::to_string(printed_host[k]) + ": cannot parse the header token '" +
+                         std::string(c, (size_t)(t - c)) + "'");
+                    return;
+                }
+                header_first_host[k] = v;
+            }
+            for (int h = 0; h < header_lines; ++h) {
+                const char* le = (const char*)memchr(s, '\n', (size_t)(end - s));
+                s = le ? le + 1 : end;
+            }
             double* out = out_host + k * nat * 3;
             for (int64_t a = 0; a < nat; ++a) {
                 const char* le = (const char*)memchr(s, '\n', (size_t)(end - s));
                 if (!le) le = end;
                 const char* c = skip_ws(s, le);
                 for (int col = 0; col < first_col; ++col) c = skip_ws(skip_tok(c, le), le);
-                const char* t = skip_tok(c, le);
-                if (t == c) { fail("frame " + std::to_string(printed_host[k]) + ": short line for atom " + std::to_string(a)); return; }
-                if (k == 0 && symbols_host) {
+                const char* t = first_col < 0 ? c : skip_tok(c, le);   // no symbol token: the numbers start here
+                if (first_col >= 0 && t == c) { fail("frame " + std::to_string(printed_host[k]) + ": short line for atom " + std::to_string(a)); return; }
+                if (k == 0 && symbols_host && first_col >= 0) {
                     size_t len = (size_t)(t - c) < 7 ? (size_t)(t - c) : 7;
                     memset(symbols_host + a * 8, 0, 8);
                     memcpy(symbols_host + a * 8, c, len);

@@ -436,26 +436,30 @@ cudaError_t launch_dd_ragged_presence(const int* fidx, const i64* lens, i64 N, i
 // acf holds Re(FFT(P_f))[k] * (1/M) for k < N (n_out = N); f = pair*7 + acc.
 __global__ void k_dd_ragged_scatter(const double* __restrict__ acf, const int* __restrict__ fidx,
                                     const i64* __restrict__ lens, i64 N, i64 nfft, double* __restrict__ G) {
-    const i64 f = blockIdx.y;
+    // series f on gridDim.x (limit 2^31 - 1; gridDim.y stops at 65535 = 9362 pairs), frame chunks on gridDim.y
+    const i64 f = blockIdx.x;
     const i64 pl = f / 7;
     const int acc = (int)(f % 7);
     const i64 np = lens[f];
     if (np <= 0) return;
     const double inv = 1.0 / (double)np;
-    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (i64)gridDim.x * blockDim.x)
+    for (i64 k = (i64)blockIdx.y * blockDim.x + threadIdx.x; k < np; k += (i64)gridDim.y * blockDim.x)
         atomicAdd(G + (i64)acc * N + fidx[pl * N + k], acf[f * N + k] * inv);
 }
 cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 nfft,
                                      double* G, cudaStream_t st) {
     if (nfft <= 0) return cudaSuccess;
-    for (i64 f0 = 0; f0 < nfft; f0 += 32767 * 7) {
-        i64 cnt = nfft - f0 < 32767 * 7 ? nfft - f0 : 32767 * 7;
-        int gx = (int)((N + 255) / 256);
-        if (gx > 64) gx = 64;
-        dim3 grid(gx, (unsigned)cnt);
+    const i64 chunk = (i64)7 << 26;   // whole pairs per launch, far below the gridDim.x limit
+    for (i64 f0 = 0; f0 < nfft; f0 += chunk) {
+        i64 cnt = nfft - f0 < chunk ? nfft - f0 : chunk;
+        int gy = (int)((N + 255) / 256);
+        if (gy > 64) gy = 64;
+        dim3 grid((unsigned)cnt, gy);
         k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf + f0 * N, fidx + (f0 / 7) * N, lens + f0, N, cnt, G);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
     }
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 // Power spectra from the engine's internal order [f][k1][k2] (k = k1 + M1 k2) to natural order [f][k2][k1]:

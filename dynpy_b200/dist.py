@@ -64,7 +64,8 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
 
 def h2d_sharded(host: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """Host -> device copy of an array every rank needs in full (the coordinates): each rank moves 1/world of
-    dim 0 over ITS host link and the blocks are then exchanged GPU to GPU (one broadcast per block: NVLink),
+    dim 0 over ITS host link and the blocks are then exchanged GPU to GPU in ONE collective
+    (``all_gather_into_tensor`` over NVLink when the blocks are equal, ``all_gather`` of views otherwise),
     instead of every rank pulling the whole array through PCIe.  Single process: a plain copy."""
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     if world == 1 or host.shape[0] < world:
@@ -73,10 +74,22 @@ def h2d_sharded(host: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     rank = dist.get_rank()
     n = host.shape[0]
     cuts = [(n * r) // world for r in range(world + 1)]
-    out[cuts[rank]:cuts[rank + 1]].copy_(host[cuts[rank]:cuts[rank + 1]], non_blocking=True)
-    for r in range(world):
-        dist.broadcast(out[cuts[r]:cuts[r + 1]], src=r)
+    mine = out[cuts[rank]:cuts[rank + 1]]
+    mine.copy_(host[cuts[rank]:cuts[rank + 1]], non_blocking=True)
+    if n % world == 0 and out.is_contiguous():
+        dist.all_gather_into_tensor(out, mine)     # in place: rank r's block is already at its final offset
+    else:
+        dist.all_gather([out[cuts[r]:cuts[r + 1]] for r in range(world)], mine)
     return out
+
+
+def broadcast_object(obj, src: int = 0):
+    """Rank `src`'s python object on every rank (single process: the object itself)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [obj]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+    return obj
 
 
 def barrier():

@@ -8,10 +8,7 @@ import time
 def user_confirm():
     start_input = time.time()
     while True:
-        try:
-            confirm = input('Continue? (Y/n)')
-        except EOFError:  # non-interactive run without piped answer: treat as the default (yes)
-            confirm = ''
+        confirm = input('Continue? (Y/n)')   # EOFError propagates on a closed stdin, as in the reference
         if confirm.lower() in ('y', 'yes', ''):
             break
         elif confirm.lower() in ('n', 'no'):

@@ -40,13 +40,20 @@ def _chk_rows(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def workspace(device, nbytes: int) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (uint8)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Grow-only scratch buffer (uint8), one per (device, current stream): kernels queued on a stream only ever
+    share scratch with later kernels of the SAME stream, and a buffer that is replaced by a larger one is
+    recorded on its stream first, so the caching allocator cannot hand its block to another stream while
+    queued kernels still use it."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(dev)
+    key = (dev, stream.cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        _WS.pop(key, None)
-        buf = None
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % key)
+        old = _WS.pop(key, None)
+        if old is not None:
+            old.record_stream(stream)
+        del old, buf
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % dev)
         _WS[key] = buf
     return buf
 

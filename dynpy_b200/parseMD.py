@@ -7,8 +7,13 @@ Mirrors ``PARSE_MD(PD, traj)`` (parseMD.py:11-65):
   * printed frames are 1-indexed, ``start_prod``..``end_prod`` inclusive, every ``sample_freq``-th;
     frame id = printed number x ``md_print_freq``; Angstrom -> bohr by ``/0.529177``;
     Fortran ``D`` exponents accepted (d_to_e, :325-329); symbols normalised by normsym (:317-323).
-  * 'QE'     : the reference's reader returns nothing (parse_qe_md has no return, :67-134), so the
-    reference itself cannot run this format; we raise a clear error instead of guessing.
+  * 'QE'     : .pos blocks of one header line ``step time`` + ``nat`` lines ``x y z`` (parse_qe_md, :67-153):
+    the directory searched is ``traj`` itself, NOT ``traj_dir + traj`` (:22); frame ids are the first token
+    of the kept header lines, not printed number x ``md_print_freq`` (:84-92); coordinates are taken as they
+    are (no Angstrom -> bohr division); symbols come from ``ParseDynamics.symbols``.  With ``parse_vel`` the
+    .vel file is read the same way from columns 1-3 (:126-127); the reference itself raises there as soon as
+    more than one frame is kept (``velatom.loc[:, 'symbol'] = symbols``, :131, a length mismatch), so that
+    branch follows the evident intent and is pinned by no reference output.
 """
 from __future__ import annotations
 
@@ -53,10 +58,12 @@ def _select_frames(start_prod, end_prod, sample_freq):
     return sel
 
 
-def _read_blocks(path, nat, header_lines, cols, printed, scale_div=1.0, pin=False):
+def _read_blocks(path, nat, header_lines, cols, printed, scale_div=1.0, pin=False, header_ids=None):
     """(symbols, xyz[F, A, 3] / scale_div) for the 1-indexed printed frames, parsed by the native
     multi-threaded reader of the C-ABI library (csrc/ingest.cpp: mmap, parallel newline index,
-    std::from_chars).  `pin` puts the array in page-locked memory for the H2D copy."""
+    std::from_chars).  `pin` puts the array in page-locked memory for the H2D copy.  cols[0] = -1: no symbol
+    token (symbols come back as None); header_ids: float64 array [F] that receives the first header token of
+    every kept block."""
     import ctypes as C
 
     from . import _lib
@@ -68,9 +75,17 @@ def _read_blocks(path, nat, header_lines, cols, printed, scale_div=1.0, pin=Fals
     else:
         host = torch.empty((F, nat, 3), dtype=torch.float64)
     sym = C.create_string_buffer(8 * nat)
-    rc = lib.dynpy_parse_md_blocks_host(os.fsencode(path), nat, header_lines, cols[0], printed.ctypes.data, F,
-                                        float(scale_div), host.data_ptr(), C.cast(sym, C.c_void_p), 0)
+    if header_ids is not None:
+        assert header_ids.dtype == np.float64 and header_ids.shape == (F,) and header_ids.flags.c_contiguous
+        rc = lib.dynpy_parse_md_blocks_hdr_host(os.fsencode(path), nat, header_lines, cols[0], printed.ctypes.data, F,
+                                                float(scale_div), host.data_ptr(), C.cast(sym, C.c_void_p),
+                                                header_ids.ctypes.data, 0)
+    else:
+        rc = lib.dynpy_parse_md_blocks_host(os.fsencode(path), nat, header_lines, cols[0], printed.ctypes.data, F,
+                                            float(scale_div), host.data_ptr(), C.cast(sym, C.c_void_p), 0)
     _lib.check(rc, "dynpy_parse_md_blocks_host")
+    if cols[0] < 0:
+        return None, host
     raw = sym.raw
     symbols = [normsym(raw[8 * a:8 * a + 8].split(b"\0", 1)[0].decode()) for a in range(nat)]
     return symbols, host
@@ -101,28 +116,38 @@ def _read_blocks_py(path, nat, header_lines, cols, printed):
     return symbols, out
 
 
-def _load_frames(path, nat, header_lines, cols, printed, device):
+def _load_frames(path, nat, header_lines, cols, printed, device, scale_div=0.529177, header_ids=None):
     """(symbols, coords [A, 3, F] on `device`) of the printed frames.  With several ranks every rank parses only
     its block of frames (the text is the expensive part), copies it over its own host link and the blocks are
-    exchanged GPU to GPU, so that every rank ends up with the whole trajectory."""
+    exchanged GPU to GPU (one all-gather), so that every rank ends up with the whole trajectory.
+    header_ids (float64 [F], optional) is filled on every rank."""
     import torch.distributed as tdist
 
     from . import dist
     rank, world = dist.rank_world()
     F = len(printed)
     if world == 1 or device.type != "cuda" or F < world:
-        sym, xyz = _read_blocks(path, nat, header_lines, cols, printed, 0.529177, pin=True)
+        sym, xyz = _read_blocks(path, nat, header_lines, cols, printed, scale_div, pin=True, header_ids=header_ids)
         # [F][A][3] (pinned host) -> device -> the kernels' [A][3][F] layout (transpose on the device)
         return sym, xyz.to(device, non_blocking=True).permute(1, 2, 0).contiguous()
     cuts = [(F * r) // world for r in range(world + 1)]
-    sym, mine = _read_blocks(path, nat, header_lines, cols, printed[cuts[rank]:cuts[rank + 1]], 0.529177, pin=True)
+    mine_ids = np.empty(cuts[rank + 1] - cuts[rank], dtype=np.float64) if header_ids is not None else None
+    sym, mine = _read_blocks(path, nat, header_lines, cols, printed[cuts[rank]:cuts[rank + 1]], scale_div, pin=True,
+                             header_ids=mine_ids)
     full = torch.empty((F, nat, 3), dtype=torch.float64, device=device)
-    full[cuts[rank]:cuts[rank + 1]].copy_(mine, non_blocking=True)
-    for r in range(world):
-        tdist.broadcast(full[cuts[r]:cuts[r + 1]], src=r)
-    box = [sym]
+    part = full[cuts[rank]:cuts[rank + 1]]
+    part.copy_(mine, non_blocking=True)
+    if F % world == 0:
+        tdist.all_gather_into_tensor(full, part)
+    else:
+        tdist.all_gather([full[cuts[r]:cuts[r + 1]] for r in range(world)], part)
+    box = [(sym, mine_ids)]
+    if header_ids is not None:
+        parts = [None] * world
+        tdist.all_gather_object(parts, mine_ids)
+        header_ids[:] = np.concatenate(parts)
     tdist.broadcast_object_list(box, src=0)   # symbols of the first printed frame, as in the single-process run
-    return box[0], full.permute(1, 2, 0).contiguous()
+    return box[0][0], full.permute(1, 2, 0).contiguous()
 
 
 def _find(traj_dir, token, what):
@@ -144,6 +169,7 @@ def PARSE_MD(PD, traj, device=None):
     fmt = PD.MD_format
     traj_dir = PD.traj_dir + traj
     printed = _select_frames(PD.start_prod, PD.end_prod, PD.sample_freq)
+    scale_div, header_ids, vcols = 0.529177, None, None
     if fmt == "xyz":
         name = _find(traj_dir, ".xyz", ".xyz")
         header, cols = 2, (0, 1, 2, 3)
@@ -155,16 +181,32 @@ def PARSE_MD(PD, traj, device=None):
         if 'symbols' not in PD.__dict__.keys():
             print("Error: Missing required input variable symbols in class ParseDynamics for parsing QE.")
             sys.exit(2)
-        raise NotImplementedError("MD_format 'QE': the reference's parse_qe_md returns nothing (parseMD.py:67-134), "
-                                  "so there is no behaviour to reproduce; convert the .pos file to xyz")
+        traj_dir = traj                       # parseMD.py:22 passes traj_dir=traj (PD.traj_dir is not prepended)
+        try:
+            name = [f for f in os.listdir(traj_dir) if ".pos" in f][0]
+        except Exception:
+            print("Did not find .pos trajectory file at " + traj_dir + " for parsing QE dynamics. Is this what you wanted?")
+            sys.exit(2)
+        if len(PD.symbols) != PD.nat:
+            # the reference sizes the blocks by len(symbols) (parseMD.py:79); nat is a required key of the CLI
+            raise ValueError("ParseDynamics.symbols lists %d atoms, nat = %d" % (len(PD.symbols), PD.nat))
+        header, cols, vcols = 1, (-1, 0, 1, 2), (0, 1, 2, 3)
+        scale_div = 1.0                       # QE coordinates are used as given (bohr)
+        header_ids = np.empty(len(printed), dtype=np.float64)
     else:
         print("MD_format not provided or not recognized. Implemented formats are 'QE', 'Tinker', and 'xyz'. "
               "Do you need to parse MD trajectories?")
         sys.exit(2)
-    sym, pos = _load_frames(os.path.join(traj_dir, name), PD.nat, header, cols, printed, device)
-    frames = printed.astype(np.int64) * int(PD.md_print_freq)
+    sym, pos = _load_frames(os.path.join(traj_dir, name), PD.nat, header, cols, printed, device, scale_div, header_ids)
+    if fmt == "QE":
+        sym = [normsym(s) for s in PD.symbols]
+        frames = header_ids.astype(np.int64)  # the step ids of the kept header lines (parseMD.py:84-92)
+        if not np.array_equal(frames.astype(np.float64), header_ids):
+            raise ValueError("non-integer step ids in the .pos headers of %s" % name)
+    else:
+        frames = printed.astype(np.int64) * int(PD.md_print_freq)
     vel = None
     if PD.parse_vel:
         vname = _find(traj_dir, ".vel", ".vel")
-        _, vel = _load_frames(os.path.join(traj_dir, vname), PD.nat, header, cols, printed, device)
+        _, vel = _load_frames(os.path.join(traj_dir, vname), PD.nat, header, vcols or cols, printed, device, scale_div)
     return Trajectory(pos=pos, symbols=sym, frames=frames, vel=vel)

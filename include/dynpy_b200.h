@@ -227,7 +227,7 @@ int dynpy_cutoff_bounds_f64(const double* y, int64_t n, int n_cols, int64_t col_
 /* ---- trajectory ingestion (HOST function; no GPU needed) -----------------------------------------
  * replaces the text handling of parseMD.parse_xyz / parse_tinker_md (parseMD.py:177-278):
  * blocks of  <header_lines> lines + nat atom lines  "[cols...] sym x y z [cols...]";
- *   first_col     column of the symbol (0: xyz, 1: Tinker .arc); x y z follow it
+ *   first_col     column of the symbol (0: xyz, 1: Tinker .arc); x y z follow it (-1: no symbol, x y z first)
  *   printed_host  1-indexed printed frame numbers to keep, ascending  [n_printed]
  *   scale_div     every value is DIVIDED by it (0.529177: Angstrom -> bohr exactly like the reference)
  *   out_host      [n_printed][nat][3] fp64 (caller-owned, may be pinned memory)
@@ -237,6 +237,16 @@ int dynpy_cutoff_bounds_f64(const double* y, int64_t n, int n_cols, int64_t col_
 int dynpy_parse_md_blocks_host(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
                                const int64_t* printed_host, int64_t n_printed, double scale_div,
                                double* out_host, char* symbols_host, int32_t n_threads);
+
+/* Same reader for the QE .pos / .vel layout of parseMD.parse_qe_md (parseMD.py:67-153): one header line
+ * "<step> <time>" per block, then nat lines "x y z" (first_col = -1: no symbol token; .vel lines carry one
+ * leading token, first_col = 0).  header_first_host (optional, [n_printed]) receives the first token of
+ * each kept block's header line as a number: the reference takes its frame ids from there
+ * (parseMD.py:84-92).  Use scale_div = 1.0: the reference does not convert QE coordinates. */
+int dynpy_parse_md_blocks_hdr_host(const char* path, int64_t nat, int32_t header_lines, int32_t first_col,
+                                   const int64_t* printed_host, int64_t n_printed, double scale_div,
+                                   double* out_host, char* symbols_host, double* header_first_host,
+                                   int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -318,6 +318,53 @@ def _sr_tinker_case(name="sr_tinker_vel"):
     print("golden:", name)
 
 
+def _write_qe(path, arr, lead=None, step=10, dt_ps=0.0001):
+    """QE (cp.x) .pos / .vel blocks: one header line 'step time' + nat lines 'x y z' in bohr as given (the reference
+    does not convert QE coordinates, parseMD.py:67-153); `lead`: one leading token per line (the .vel reader takes
+    columns 1-3, :127)."""
+    a = arr.numpy()
+    with open(path, "w") as fh:
+        for f in range(a.shape[2]):
+            fh.write("   %d   %.8f\n" % ((f + 1) * step, (f + 1) * step * dt_ps))
+            for k in range(a.shape[0]):
+                x, y, z = a[k, :, f]
+                fh.write("%s %.10f %.10f %.10f\n" % (lead[k] if lead else "", x, y, z))
+
+
+def _qe_cases():
+    """MD_format = 'QE' (parse_qe_md, parseMD.py:67-153): the trajectory directory is `traj` itself, frame ids come
+    from the .pos header lines (10, 20, ... here, NOT printed number x md_print_freq), no unit conversion, symbols
+    from the parameter class.  sr_qe: 6 waters, sampled frames, velocities by finite difference; dd_qe: 8 waters.
+    (parse_vel = True is not a case: the reference raises at parseMD.py:131 for more than one kept frame.)"""
+    sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv", "{traj}/Jacfs_all.csv",
+              "{traj}/Jacf.csv", "SR-results.csv"]
+    for name, box, nprinted, start, end, samp, flag, extra, outputs in (
+            ("sr_qe", synth.water_box(6, seed=21), 26, 2, 26, 2, "-s",
+             "class SpinRotation:\n    mol_type = 'water'\n    nmol = 6\n    C_SR = [36.9, 33.5, 35.5]\n", sr_out),
+            ("dd_qe", synth.water_box(8, seed=2, drift=0.02), 40, 1, 40, 1, "-d",
+             "class Dipolar:\n    identifier = 'H(2)O(1)'\n    pair_type = 'all'\n    rmax = 9.0\n",
+             ["{traj}/avg-acf.csv", "DD-results.csv"])):
+        case = os.path.join(GOLD, name)
+        shutil.rmtree(case, ignore_errors=True)
+        os.makedirs(os.path.join(case, "01"))
+        _write_qe(os.path.join(case, "01", "md.pos"), box.frames(0, nprinted))
+        body = PD_TMPL.format(trajs=["01"], nat=box.nat, start=start, end=end, mdp=7, samp=samp, celldm=box.celldm,
+                              dt=0.001)
+        body = body.replace("MD_format = 'xyz'", "MD_format = 'QE'") + "    symbols = %r\n" % (box.symbols,) + extra
+        synth.write_params(os.path.join(case, "params.py"), body)
+        with tempfile.TemporaryDirectory() as tmp:
+            work = os.path.join(tmp, "w")
+            shutil.copytree(case, work)
+            out = refshim.run_cli(flag, "params.py", cwd=work)
+            os.makedirs(os.path.join(case, "ref"))
+            with open(os.path.join(case, "ref", "stdout.txt"), "w") as fh:
+                fh.write(out)
+            for rel in outputs:
+                r = rel.format(traj="01")
+                shutil.copy(os.path.join(work, r), os.path.join(case, "ref", r.replace("/", "__")))
+        print("golden:", name)
+
+
 def _dd_dynamic_cases():
     """6 waters in a small box: in one sampled frame two molecules touch (an H-H contact inside the bond
     cut-off), so the per-frame molecule detection merges them there.  'all' pairs do not depend on molecules;
@@ -366,6 +413,8 @@ def main():
         return _qr_case("qr_nan", **_QR_NAN)
     if "--dd-dynamic-only" in sys.argv:
         return _dd_dynamic_cases()
+    if "--qe-only" in sys.argv:
+        return _qe_cases()
     if "--dd-hetero-only" in sys.argv:
         return _dd_hetero_case()
     if "--sr-ar-only" in sys.argv:
@@ -402,6 +451,7 @@ def main():
     _dd_hetero_case()
     _dd_dynamic_cases()
     _sr_tinker_case()
+    _qe_cases()
 
     sr_out = ["{traj}/molax.csv", "{traj}/ang_vel_molax.csv", "{traj}/J_cart.csv",
               "{traj}/Jacfs_all.csv", "{traj}/Jacf.csv", "SR-results.csv"]

@@ -300,6 +300,67 @@ def test_dd_full_size_properties(ops):
     np.testing.assert_allclose(G0, ref, rtol=1e-10)
 
 
+@pytest.mark.parametrize("F,P,m1", [
+    (1_000_000, 5, 512),   # cfg5 frame count: M = 2^21, the long-column kernel, odd pair count
+    (600_000, 3, 512),     # M = 2^21 with the second half of the 512-point columns partly empty
+    (140_000, 3, 128),     # M = 2^19
+    (270_000, 3, 256),     # M = 2^20
+])
+def test_dd_long_series_full_acf_vs_oracle(ops, F, P, m1):
+    """FULL summed ACFs (every lag, all 7 columns) of the fused dipolar call at the long transform lengths
+    (M1 = 128, 256, 512; cfg5 is 1e6 frames = M 2^21) against orc.dd_pairs_gapless: normwise <= 1e-10."""
+    from dynpy_b200 import synth
+    box = synth.water_box(4, seed=5, drift=0.01, trans_amp=0.2).to("cuda")
+    hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
+    L = box.celldm
+    w = ops.wrap(box.trajectory(F, chunk=1 << 16, atom_mask=hidx), L)
+    i, j = np.triu_indices(8, k=1)
+    sel = [0, 9, 13, 20, 27][:P]          # an intramolecular pair and intermolecular ones
+    i, j = i[sel], j[sel]
+    M = ops.fft_length(F)
+    assert M == m1 * 4096
+    spec = ops.dd_pairs_to_spectrum(w, dev(i, torch.int32), dev(j, torch.int32), (L, L, L), M=M)
+    G = ops.ifft_acf(spec, F, 1.0 / (float(M) * F)).cpu().numpy()
+    ref = orc.dd_pairs_gapless(w.cpu().numpy(), list(zip(i.tolist(), j.tolist())), L)
+    scale = max(np.max(np.abs(ref[c])) for c in (4, 5, 6))
+    for c in range(7):
+        denom = np.max(np.abs(ref[c])) if c != 3 else max(np.max(np.abs(ref[3])), 1e-6 * scale)
+        err = np.max(np.abs(G[c] - ref[c])) / denom
+        assert err < 1e-10, (c, err)
+
+
+def test_dd_ragged_more_than_9362_pairs_per_batch(ops):
+    """Short trajectory, normal-size box, rmax = 15 bohr: one ragged batch holds > 9362 partial pairs
+    (65535 / 7 series: the old gridDim.y limit of the scatter launch).  Checked against the same call cut
+    into small batches, and against the oracle on a subset of the pairs."""
+    from dynpy_b200 import synth
+    F = 48
+    box = synth.water_box(64, seed=7, drift=0.02).to("cuda")
+    hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
+    L = box.celldm
+    w = ops.wrap(box.trajectory(F, chunk=64, atom_mask=hidx), L)
+    i, j = np.triu_indices(128, k=1)
+    keep = np.arange(len(i)) % 7 != 3
+    i, j = i[keep][:11000], j[keep][:11000]
+    assert len(i) > 9362
+    pi, pj = dev(i, torch.int32), dev(j, torch.int32)
+    cell = (L, L, L)
+    big = ops.dd_pairs_ragged_to_acf(w, pi, pj, cell, 15.0, ws_budget=8 << 30)
+    small = torch.zeros_like(big)
+    for s0 in range(0, len(i), 3000):
+        ops.dd_pairs_ragged_to_acf(w, pi[s0:s0 + 3000].contiguous(), pj[s0:s0 + 3000].contiguous(), cell, 15.0, G=small,
+                                   ws_budget=64 << 20)
+    scale = big.abs().amax(dim=1, keepdim=True)
+    assert float(((big - small).abs() / scale).max()) < 1e-12
+    sub = slice(5000, 5040)
+    got = ops.dd_pairs_ragged_to_acf(w, pi[sub].contiguous(), pj[sub].contiguous(), cell, 15.0).cpu().numpy()
+    ref = orc.dd_pairs_ragged(w.cpu().numpy(), list(zip(i[sub].tolist(), j[sub].tolist())), L, 15.0)
+    scale = max(np.max(np.abs(ref[c])) for c in (4, 5, 6))
+    for c in range(7):
+        denom = np.max(np.abs(ref[c])) if c != 3 else max(np.max(np.abs(ref[3])), 1e-6 * scale)
+        assert np.max(np.abs(got[c] - ref[c])) / denom < 1e-10, c
+
+
 def test_dd_cfg5_frame_count_properties(ops):
     """cfg5 frame count (1e6 frames, M = 2^21, 512-point column transforms): lag 0 and a few scattered lags of
     the summed ACFs against direct O(N) sums of independently formed series, and additivity over pair sets."""

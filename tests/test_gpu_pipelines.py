@@ -101,7 +101,8 @@ def test_qr_golden_iodide_rates_on_gpu(ops):
 @pytest.mark.parametrize("case,trajs", [("dd_gapless_all", ["01"]), ("dd_gaps_inter", ["01"]),
                                          ("dd_intra_sampled", ["01", "02"]), ("dd_analyte_label", ["01"]),
                                          ("dd_hetero_13C", ["01"]), ("dd_dynamic_all", ["01"]),
-                                         ("dd_dynamic_inter", ["01"]), ("dd_dynamic_intra", ["01"])])
+                                         ("dd_dynamic_inter", ["01"]), ("dd_dynamic_intra", ["01"]),
+                                         ("dd_qe", ["01"])])
 def test_cli_ddrelax_vs_reference_csv(tmp_path, case, trajs, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-d", work)
@@ -195,7 +196,7 @@ def test_topology_change_is_detected(ops):
 
 # ------------------------------------------------------------------ SR
 @pytest.mark.parametrize("case", ["sr_methane", "sr_water", "sr_methane_ar", "sr_methyl", "sr_methyl_global", "sr_ring",
-                                  "sr_tinker_vel"])
+                                  "sr_tinker_vel", "sr_qe"])
 def test_cli_srrelax_vs_reference_csv(tmp_path, case, ops):
     work = _workdir(tmp_path, case)
     out = _run_cli("-s", work)

@@ -163,6 +163,51 @@ def test_native_block_reader_matches_python_reader(tmp_path):
         parseMD._read_blocks(str(bad), 1, 2, (0, 1, 2, 3), np.array([1]))
 
 
+def test_parse_qe_pos_and_vel(tmp_path):
+    """MD_format = 'QE' (parseMD.py:67-153): the directory is `traj` itself (not traj_dir + traj), frame ids are the
+    step numbers of the kept .pos header lines, coordinates are not converted, symbols come from the parameter
+    class; .vel values sit in columns 1-3.  The committed fixture the reference ran (sr_qe) is parsed too."""
+    from dynpy_b200 import parseMD
+    rng = np.random.default_rng(9)
+    nat, nfr = 5, 12
+    pos = rng.normal(size=(nfr, nat, 3)) * 7
+    vel = rng.normal(size=(nfr, nat, 3))
+    d = tmp_path / "run7"
+    d.mkdir()
+    with open(d / "h2o.pos", "w") as fp, open(d / "h2o.vel", "w") as fv:
+        for f in range(nfr):
+            fp.write("  %d   %.6f\n" % (50 * (f + 1), 0.0121 * (f + 1)))
+            fv.write("  %d   %.6f\n" % (50 * (f + 1), 0.0121 * (f + 1)))
+            for a in range(nat):
+                fp.write("  %.17g %.17g %.17g\n" % tuple(pos[f, a]))
+                fv.write("H  %.17g %.17g %.17g\n" % tuple(vel[f, a]))
+
+    class PD:
+        MD_format = "QE"; traj_dir = "/nonexistent/"; trajs = [str(d)]; nat = 5; start_prod = 3; end_prod = 11
+        md_print_freq = 1000; sample_freq = 4; celldm = 20.0; timestep = 0.001; parse_vel = True
+        symbols = ["O", "H", "H", "Na", "Cl"]
+    tr = parseMD.PARSE_MD(PD, str(d), device=torch.device("cpu"))
+    assert tr.symbols == PD.symbols
+    np.testing.assert_array_equal(tr.frames, [150, 350, 550])          # header step ids, no md_print_freq
+    np.testing.assert_array_equal(tr.pos.numpy(), pos[[2, 6, 10]].transpose(1, 2, 0))   # bit-exact, no unit change
+    np.testing.assert_array_equal(tr.vel.numpy(), vel[[2, 6, 10]].transpose(1, 2, 0))
+    # the fixture the unmodified reference ran: 6 waters, printed frames 2..26 step 2, header ids 10 x printed
+    cwd = os.getcwd()
+    os.chdir(os.path.join(GOLDEN, "sr_qe"))
+    try:
+        P = load_params("sr_qe").ParseDynamics
+        tr = parseMD.PARSE_MD(P, "01", device=torch.device("cpu"))
+    finally:
+        os.chdir(cwd)
+    np.testing.assert_array_equal(tr.frames, np.arange(2, 27, 2) * 10)
+    assert tr.pos.shape == (18, 3, 13) and tr.symbols == P.symbols
+
+    class Bad(PD):
+        symbols = ["O", "H"]
+    with pytest.raises(ValueError, match="symbols lists 2 atoms"):
+        parseMD.PARSE_MD(Bad, str(d), device=torch.device("cpu"))
+
+
 # ------------------------------------------------------------------ topology / pair indexing
 def test_topology_numbering_and_pair_selection_match_oracle():
     from dynpy_b200 import DDparse, synth, topology
