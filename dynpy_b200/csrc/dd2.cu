@@ -4,6 +4,7 @@
 #include "dd_tpc.cuh"
 #include "fft_rows2.cuh"
 #include "kernels.h"
+#include <stdint.h>
 #include <stdlib.h>
 
 namespace dynpy {
@@ -41,7 +42,22 @@ static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_
     int gy = (4 * per_sm * n_sm + tiles - 1) / tiles;   // >= 4 waves
     if (gy > p.items) gy = (int)p.items;
     if (gy < 1) gy = 1;
-    k_cols_tpc2<B, C><<<dim3(tiles, gy), B * C, smem, st>>>(p, tw);
+    static int v3 = -1;
+    if (v3 < 0) { const char* en = getenv("DYNPY_TPC2"); v3 = (en && en[0] == 'o') ? 0 : 1; }   // "old": per-series loads (A/B)
+    if (v3) {
+        static int per = -1;
+        if (per < 0) { const char* en = getenv("DYNPY_TPC3_PER_SM"); per = en ? atoi(en) : 3; }
+        const size_t smem3 = smem + (size_t)16 * B * sizeof(cd);
+        auto kern = per == 2 ? k_cols_tpc3<B, C, 2> : k_cols_tpc3<B, C, 3>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+        if (e != cudaSuccess) return e;
+        gy = (4 * per * n_sm + tiles - 1) / tiles;
+        if (gy > p.items) gy = (int)p.items;
+        if (gy < 1) gy = 1;
+        kern<<<dim3(tiles, gy), B * C, smem3, st>>>(p, tw);
+    } else {
+        k_cols_tpc2<B, C><<<dim3(tiles, gy), B * C, smem, st>>>(p, tw);
+    }
     return cudaGetLastError();
 }
 
@@ -191,7 +207,13 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
             gp.n_slots = 2 * cnt;
             {
                 ProfScope prof(PROF_WORDS, st);
-                k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
+                // N % 4 == 0: 32-byte loads / stores (every stream is 32-byte aligned then); DYNPY_DD_GEOM=scalar for A/B
+                static int vec = -1;
+                if (vec < 0) { const char* e = getenv("DYNPY_DD_GEOM"); vec = (e && e[0] == 's') ? 0 : 1; }
+                if (vec && (N & 3) == 0 && ((uintptr_t)X & 31) == 0)
+                    k_dd_geom4<<<dim3((unsigned)((N + 2047) / 2048), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
+                else
+                    k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
             }
             DYNPY_CHECK(cudaGetLastError(), "dd geometry");
             tp.items = cnt;

@@ -89,6 +89,87 @@ __global__ void __launch_bounds__(256) k_dd_geom(const GeomParams p) {
     }
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): four consecutive frames of one coordinate stream per load,
+// two output points per store
+__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(cd* p, cd a, cd b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
+// The same kernel for N % 4 == 0 (every stream of every atom then starts on a 32-byte boundary): a thread owns
+// 2 x 4 consecutive frames; its 12 loads of 32 bytes (6 coordinate streams x 2) are all issued before the first
+// use, so a warp keeps 12 KB in flight instead of 4 x 6 scalar loads of 8 bytes with the arithmetic between
+// them; the two output streams are written with 32-byte stores.
+// grid: (frame chunks of 2048, pair slots); 256 threads x 2 x 4 frames
+__global__ void __launch_bounds__(256) k_dd_geom4(const GeomParams p) {
+    __shared__ double sred[8];
+    const i64 slot = blockIdx.y;
+    const i64 pr = p.pair0 + slot;
+    const bool exists = pr < p.n_pairs;
+    const double* xi = p.X;
+    const double* xj = p.X;
+    if (exists) {
+        xi += (i64)__ldg(p.pi + pr) * 3 * p.N;
+        xj += (i64)__ldg(p.pj + pr) * 3 * p.N;
+    }
+    cd* out = p.Gs + slot * 2 * p.N;
+    const double L[3] = {p.a, p.b, p.c};
+    double rs = 0.0;
+    double ci[2][3][4], cj[2][3][4];
+    i64 f0[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        f0[e] = (i64)blockIdx.x * 2048 + e * 1024 + threadIdx.x * 4;
+        if (f0[e] < p.N && exists) {
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                ldg256(xi + ax * p.N + f0[e], ci[e][ax]);
+                ldg256(xj + ax * p.N + f0[e], cj[e][ax]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (f0[e] < p.N) {
+            cd g0[4], g1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double gx = 0.0, gy = 0.0, gz = 0.0, g3 = 0.0;
+                if (exists) {
+                    double d[3], s2[3];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) axis_min(ci[e][ax][q], cj[e][ax][q], L[ax], d[ax], s2[ax]);
+                    const double r2 = __dadd_rn(__dadd_rn(s2[0], s2[1]), s2[2]);
+                    double rinv = rsqrt(r2);
+                    rinv = rinv * fma(-0.5 * r2, rinv * rinv, 1.5);  // one Newton step: r^-1 to ~1 ulp
+                    gx = d[0] * rinv; gy = d[1] * rinv; gz = d[2] * rinv;
+                    g3 = rinv * rinv * rinv;
+                }
+                g0[q] = make_double2(gx, gy);
+                g1[q] = make_double2(gz, g3);
+                rs += g3;
+            }
+            stg256(out + f0[e], g0[0], g0[1]);
+            stg256(out + f0[e] + 2, g0[2], g0[3]);
+            stg256(out + p.N + f0[e], g1[0], g1[1]);
+            stg256(out + p.N + f0[e] + 2, g1[2], g1[3]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = rs;
+    __syncthreads();
+    if (threadIdx.x == 0 && exists) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sred[w];
+        atomicAdd(p.rsum + slot, t);
+    }
+}
+
 struct ColsTpcParams {
     const cd* Gs;      // [2*items][2][N] geometry streams of the batch (nullptr: all-ones series, "ones" mode)
     i64 items;
@@ -408,6 +489,129 @@ __global__ void __launch_bounds__(B * C, 384 / (B * C)) k_cols_tpc2(const ColsTp
                     const cd y = (c & 1) ? v[c >> 1] : e[c >> 1];
                     smem[(c * B + bA) * C + colA] = cmul(y, w);
                     if (c < 15) w = cmul(w, tb);
+                }
+            }
+            __syncthreads();
+            // ---- phase C: B-point transform over b for (c, column), parity `par`
+            cd u[HB];
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const cd y0 = smem[(cC * B + j) * C + colC];
+                const cd y1 = smem[(cC * B + j + HB) * C + colC];
+                u[j] = par ? make_double2(y0.x - y1.x, y0.y - y1.y) : make_double2(y0.x + y1.x, y0.y + y1.y);
+            }
+            __syncthreads();   // the buffer may be rewritten by the next series
+            if (par) Tpc2Codelets<B>::odd(u); else Tpc2Codelets<B>::even(u);
+            cd* dst = p.T + (item * 11 + slot) * TS + n2C;
+            {
+                cd w = seed;
+#pragma unroll
+                for (int dd = 0; dd < HB; ++dd) {
+                    const int k1 = cC + 16 * (2 * dd + par);
+                    st_stream(dst + (i64)k1 * DYNPY_T_RS, cmul(u[dd], w));
+                    if (dd + 1 < HB) w = cmul(w, step);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- long columns, geometry held in registers
+// Same two-level transform as k_cols_tpc2, reorganised around what its profile showed (exposed load latency at
+// the top of every series, 37 % issue utilisation): the 8 frames a phase-A thread needs are THE SAME for all 11
+// series of an item, so the four geometry streams are loaded once per item into registers (32 loads of 16 bytes
+// in flight per thread, one exposed latency per item instead of per series, 1/11 of the L2 traffic) and the 11
+// series are formed from them.  The phase-A twiddles W_M1^{b c} are loop-invariant per thread: they come from a
+// 16 x B table in shared memory (the C column threads of one b read the same entry: one wavefront per warp
+// load) instead of a 14-product chain per series.
+template <int B, int C, int PER_SM>
+__global__ void __launch_bounds__(B * C, PER_SM) k_cols_tpc3(const ColsTpcParams p, const cd* __restrict__ twp) {
+    static_assert(B == 32, "phase A (B x C threads) and phase C (16 x 2 x C threads) use the same threads only for B = 32");
+    constexpr int M1 = 16 * B;
+    constexpr int HB = B / 2;
+    extern __shared__ double2 smem[];  // S[c][b][col] (16 * B * C entries), then TA[c][b] (16 * B entries)
+    cd* TA = smem + 16 * B * C;
+    const int tid = threadIdx.x;
+    const i64 N = p.N;
+    const int nfr = (int)(N < (i64)(M1 / 2) * 4096 ? N : (i64)(M1 / 2) * 4096);
+    const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
+    const double KF = 1.5853309190424043;
+    constexpr i64 TS = (i64)M1 * DYNPY_T_RS;
+    const int tile = blockIdx.x;
+    const int colA = tid % C, bA = tid / C;
+    const int n2A = tile * C + colA;
+    const int colC = tid % C, par = (tid / C) & 1, cC = tid / (2 * C);
+    const int n2C = tile * C + colC;
+    const double inv_M = 1.0 / (double)p.M;
+    const cd seed = w_exact(((i64)n2C * (cC + 16 * par)) % p.M, inv_M);   // W_M^{n2 (c + 16 p)}
+    const cd step = w_exact(((i64)n2C * 32) % p.M, inv_M);                // W_M^{32 n2}
+    for (int e = tid; e < 16 * B; e += B * C) TA[e] = ldg_cd(twp + (e / B) * (e % B) * (4096 / M1));   // W_M1^{b c}
+    __syncthreads();
+    // frames of this thread's residue: (B a + b) 4096 + n2, a = 0..7
+    unsigned onmask = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) onmask |= ((i64)(B * a + bA) * 4096 + n2A < nfr) ? (1u << a) : 0u;
+
+    for (i64 item = blockIdx.y; item < p.items; item += gridDim.y) {
+        const cd* g = p.Gs + item * 4 * N;
+        const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
+        const double mp = __ldg(p.rsum + 2 * item) * p.inv_n;
+        const double mq = __ldg(p.rsum + 2 * item + 1) * p.inv_n;
+        // series in three groups that share their two streams: complex series of p (streams 0, 1), of q (2, 3),
+        // packed real series of p + i q (1, 3)
+        cd GA[8], GB[8];
+#pragma unroll 1
+        for (int idx = 0; idx < 11; ++idx) {
+            const int slot = idx < 8 ? ((idx & 3) == 0 ? 1 : (idx & 3) == 1 ? 3 : (idx & 3) == 2 ? 7 : 9) + (idx >> 2)
+                                     : (idx == 8 ? 0 : idx - 4);
+            if (idx == 0 || idx == 4 || idx == 8) {
+                const cd* sa = g + (idx == 0 ? 0 : idx == 4 ? 2 : 1) * N;
+                const cd* sb = g + (idx == 0 ? 1 : 3) * N;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
+                    const bool on = (onmask >> a) & 1u;
+                    const cd zero = make_double2(0.0, 0.0);
+                    GA[a] = on ? ldg_cd(sa + fr) : zero;
+                    GB[a] = on ? ldg_cd(sb + fr) : zero;
+                }
+            }
+            // ---- phase A: the 8 samples of residue b
+            cd v[8];
+            if (idx >= 8) {           // real series of p and q packed as re + i im; GA, GB = (z/r, r^-3) of p, q
+                const double c = slot == 5 ? 1.0 : (slot == 6 ? KF * C20 : C20);
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const bool on = (onmask >> a) & 1u;
+                    const double yp = slot == 5 ? 1.0 : fma(3.0 * GA[a].x, GA[a].x, -1.0);
+                    const double yq = slot == 5 ? 1.0 : fma(3.0 * GB[a].x, GB[a].x, -1.0);
+                    const double sp = slot == 0 ? c : c * GA[a].y, sq = slot == 0 ? c : c * GB[a].y;
+                    v[a].x = on ? sp * yp - (slot == 5 ? mp : 0.0) : 0.0;
+                    v[a].y = (on && q_exists) ? sq * yq - (slot == 5 ? mq : 0.0) : 0.0;
+                }
+            } else {                  // GA = (x, y)/r, GB = (z/r, r^-3) of the series' pair
+                const bool weighted = slot >= 7;
+                const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;
+                const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const cd xy = GA[a], zr = GB[a];
+                    const cd w = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                    const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
+                    v[a] = make_double2(sc * w.x, sc * w.y);
+                }
+            }
+            {
+                cd e[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) e[a] = v[a];
+                fft8(e);        // y[2 c']
+                fft8_odd(v);    // y[2 c' + 1]
+                smem[(0 * B + bA) * C + colA] = e[0];
+#pragma unroll
+                for (int c = 1; c < 16; ++c) {
+                    const cd y = (c & 1) ? v[c >> 1] : e[c >> 1];
+                    smem[(c * B + bA) * C + colA] = cmul(y, TA[c * B + bA]);
                 }
             }
             __syncthreads();

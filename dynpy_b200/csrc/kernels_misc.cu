@@ -252,29 +252,109 @@ cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const in
 // the bond flag of the reference frame?  (The reference re-detects bonds/molecules in every
 // frame, distances.py:244-257 + universe.py:411-451; the CUDA path indexes molecules once and
 // verifies here that this is equivalent.)  out[0] = number of mismatching pair-frames,
-// out[1] = first frame with a mismatch.
-__global__ void __launch_bounds__(256)
+// out[1] = first frame with a mismatch, out[2] = number of events listed.
+//
+// O(A^2 F) pair-frames, but almost all of them are far apart: a thread owns one frame and a tile of
+// TOPO_TI atoms i whose x coordinates stay in registers; for every j it loads x_j once (a coalesced 1 KB run
+// per warp... consecutive threads = consecutive frames) and screens the TI pairs with three fp64 instructions
+// each — nearest-image |dx| against T = the largest bond threshold; y and z are loaded and screened only for
+// the pairs that pass (lanes of a warp are consecutive frames of the SAME pair, so the branches are nearly
+// uniform).  Only pairs inside the T-cube (a fraction (2T/L)^3) take the exact path: the bit-exact per-axis
+// minimum image of the pair kernels and the reference's comparison.  The expected bonds of the tile's atoms are
+// listed in shared memory once per CTA and verified in every frame first, so the screened sweep only has to
+// find bonds that are NOT expected.  Coordinates are swept A / TOPO_TI times through L2 (the CTAs of one
+// frame chunk are adjacent in the grid) instead of A / 2 times.
+#define TOPO_TI 8
+#define TOPO_NT 128
+#define TOPO_BCAP 128
+__device__ __forceinline__ bool topo_bond_exact(const double* __restrict__ X, i64 N, i64 n, i64 i, i64 j, double ri,
+                                                double rj, double extra, double a, double b, double c, double dmax2) {
+    double d, sx, sy, sz;
+    axis_min(X[(i * 3 + 0) * N + n], __ldg(X + (j * 3 + 0) * N + n), a, d, sx);
+    axis_min(X[(i * 3 + 1) * N + n], __ldg(X + (j * 3 + 1) * N + n), b, d, sy);
+    axis_min(X[(i * 3 + 2) * N + n], __ldg(X + (j * 3 + 2) * N + n), c, d, sz);
+    const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+    return (r2 < dmax2) && (sqrt(r2) <= __dadd_rn(__dadd_rn(ri, rj), extra));
+}
+// Is the nearest of the images -1, 0, +1 along one axis possibly within T?  min(|d|, ||d| - a|) <= T  is implied
+// by  ||d| - a/2| >= a/2 - T  (equivalent for |d| <= a, a superset beyond): three fp64 instructions, no fmin
+// (which costs a DSETP + two selects + NaN fix-up here).  h = a / 2, thr = a / 2 - T.
+__device__ __forceinline__ bool topo_axis_near(double xi, double xj, double h, double thr) {
+    return fabs(fabs(xi - xj) - h) >= thr;
+}
+__global__ void __launch_bounds__(TOPO_NT)
 k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
                  const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
-                 unsigned long long* __restrict__ out, i64* __restrict__ events, i64 cap) {
-    const i64 n = (i64)blockIdx.x * 256 + threadIdx.x;
-    const i64 i = blockIdx.y;
+                 const double* __restrict__ Tscreen, i64 tiles, unsigned long long* __restrict__ out,
+                 i64* __restrict__ events, i64 cap) {
+    __shared__ int s_nb;
+    __shared__ unsigned s_bond[TOPO_BCAP];   // (k << 24) | j : expected bonds (i0 + k, j), j > i0 + k
+    // 1-D grid, atom tiles fastest: the CTAs of one frame chunk are adjacent and share its coordinates in L2
+    const i64 chunk = blockIdx.x / tiles;
+    const i64 n = chunk * TOPO_NT + threadIdx.x;
+    const i64 i0 = (blockIdx.x - chunk * tiles) * TOPO_TI;
+    const double T = *Tscreen;
+    const double ha = 0.5 * a, hb = 0.5 * b, hc = 0.5 * c;
+    const double ta = ha - T, tb = hb - T, tc = hc - T;
+    const int ti = (int)(A - i0 < TOPO_TI ? A - i0 : TOPO_TI);
+    if (threadIdx.x == 0) s_nb = 0;
+    __syncthreads();
+    for (int k = 0; k < ti; ++k) {
+        const unsigned char* row = expect + (i0 + k) * A;
+        for (i64 j = i0 + k + 1 + threadIdx.x; j < A; j += TOPO_NT)
+            if (row[j]) {
+                const int p = atomicAdd(&s_nb, 1);
+                if (p < TOPO_BCAP) s_bond[p] = ((unsigned)k << 24) | (unsigned)j;
+            }
+    }
+    __syncthreads();
+    const int nb = s_nb;
+    const bool listed = nb <= TOPO_BCAP && A < (1 << 24);   // else: expected flags are read from global memory
     if (n >= N) return;
-    const double xi = X[(i * 3 + 0) * N + n], yi = X[(i * 3 + 1) * N + n], zi = X[(i * 3 + 2) * N + n];
-    const double ri = rcov[i];
     unsigned long long bad = 0;
-    for (i64 j = i + 1; j < A; ++j) {
-        double d, sx, sy, sz;
-        axis_min(xi, __ldg(X + (j * 3 + 0) * N + n), a, d, sx);
-        axis_min(yi, __ldg(X + (j * 3 + 1) * N + n), b, d, sy);
-        axis_min(zi, __ldg(X + (j * 3 + 2) * N + n), c, d, sz);
-        const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
-        const bool bond = (r2 < dmax2) && (sqrt(r2) <= __dadd_rn(__dadd_rn(ri, rcov[j]), extra));
-        if (bond != (expect[i * A + j] != 0)) {
-            ++bad;
-            if (events) {  // (frame, i, j) of every bond flag that differs from the indexing frame's
-                const unsigned long long k = atomicAdd(out + 2, 1ull);
-                if ((i64)k < cap) { events[3 * k] = n; events[3 * k + 1] = i; events[3 * k + 2] = j; }
+    auto report = [&](i64 i, i64 j) {
+        ++bad;
+        if (events) {  // (frame, i, j) of every bond flag that differs from the indexing frame's
+            const unsigned long long k = atomicAdd(out + 2, 1ull);
+            if ((i64)k < cap) { events[3 * k] = n; events[3 * k + 1] = i; events[3 * k + 2] = j; }
+        }
+    };
+    // ---- expected bonds must be bonds in this frame
+    if (listed) {
+        for (int q = 0; q < nb; ++q) {
+            const i64 i = i0 + (s_bond[q] >> 24), j = s_bond[q] & 0xffffffu;
+            if (!topo_bond_exact(X, N, n, i, j, rcov[i], rcov[j], extra, a, b, c, dmax2)) report(i, j);
+        }
+    } else {
+        for (int k = 0; k < ti; ++k)
+            for (i64 j = i0 + k + 1; j < A; ++j)
+                if (expect[(i0 + k) * A + j] &&
+                    !topo_bond_exact(X, N, n, i0 + k, j, rcov[i0 + k], rcov[j], extra, a, b, c, dmax2))
+                    report(i0 + k, j);
+    }
+    // ---- screened sweep: bonds that are not expected
+    double xi[TOPO_TI];
+#pragma unroll
+    for (int k = 0; k < TOPO_TI; ++k) xi[k] = k < ti ? X[((i0 + k) * 3 + 0) * N + n] : 0.0;
+    for (i64 j = i0 + 1; j < A; ++j) {
+        const double xj = __ldg(X + (j * 3 + 0) * N + n);
+        unsigned near = 0;
+#pragma unroll
+        for (int k = 0; k < TOPO_TI; ++k)
+            if (topo_axis_near(xi[k], xj, ha, ta)) near |= 1u << k;
+        if (j - i0 < TOPO_TI) near &= (1u << (j - i0)) - 1u;   // pairs with i0 + k < j only
+        near &= (1u << ti) - 1u;
+        if (near) {
+            const double yj = __ldg(X + (j * 3 + 1) * N + n);
+            const double zj = __ldg(X + (j * 3 + 2) * N + n);
+            while (near) {
+                const int k = __ffs(near) - 1;
+                near &= near - 1;
+                const i64 i = i0 + k;
+                if (!topo_axis_near(X[(i * 3 + 1) * N + n], yj, hb, tb)) continue;
+                if (!topo_axis_near(X[(i * 3 + 2) * N + n], zj, hc, tc)) continue;
+                if (topo_bond_exact(X, N, n, i, j, rcov[i], rcov[j], extra, a, b, c, dmax2) && !expect[i * A + j])
+                    report(i, j);
             }
         }
     }
@@ -283,13 +363,39 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
         atomicMin(out + 1, (unsigned long long)n);
     }
 }
+// screening radius of k_topology_check: the largest bond threshold any pair can have (2 max rcov + extra, never
+// more than dmax), with a margin that covers the rounding of the screen's own subtractions
+__global__ void k_topo_screen_radius(const double* __restrict__ rcov, i64 n, double extra, double dmax,
+                                     double* __restrict__ out) {
+    double m = 0.0;
+    for (i64 k = threadIdx.x; k < n; k += blockDim.x) m = fmax(m, rcov[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    __shared__ double sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+        double T = fmin(2.0 * m + extra, dmax);
+        if (!(T > 0.0)) T = 0.0;
+        *out = T * (1.0 + 1e-9) + 1e-9;
+    }
+}
 cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
                                   unsigned long long* out, i64* events, i64 cap, cudaStream_t st) {
     if (A < 2 || N < 1) return cudaSuccess;
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)(A - 1));
-    k_topology_check<<<grid, 256, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax, out, events, cap);
-    return cudaGetLastError();
+    const i64 tiles = (A + TOPO_TI - 1) / TOPO_TI, chunks = (N + TOPO_NT - 1) / TOPO_NT;
+    if (tiles * chunks > 0x7fffffffll) return cudaErrorInvalidValue;
+    double* T = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&T, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    k_topo_screen_radius<<<1, 256, 0, st>>>(rcov, A, extra, dmax, T);
+    k_topology_check<<<(unsigned)(tiles * chunks), TOPO_NT, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax,
+                                                                      T, tiles, out, events, cap);
+    e = cudaGetLastError();
+    cudaFreeAsync(T, st);   // stream-ordered: released after the kernel above has run
+    return e;
 }
 
 // ddrax.cart_to_dipolar_from_df (ddrax.py:110-126) as a stand-alone call: pair vectors -> the 11 real words

@@ -335,11 +335,11 @@ def test_dd_ragged_more_than_9362_pairs_per_batch(ops):
     into small batches, and against the oracle on a subset of the pairs."""
     from dynpy_b200 import synth
     F = 48
-    box = synth.water_box(64, seed=7, drift=0.02).to("cuda")
+    box = synth.water_box(96, seed=7, drift=0.02).to("cuda")
     hidx = torch.tensor([k for k, s in enumerate(box.symbols) if s == "H"], device="cuda")
     L = box.celldm
     w = ops.wrap(box.trajectory(F, chunk=64, atom_mask=hidx), L)
-    i, j = np.triu_indices(128, k=1)
+    i, j = np.triu_indices(192, k=1)
     keep = np.arange(len(i)) % 7 != 3
     i, j = i[keep][:11000], j[keep][:11000]
     assert len(i) > 9362
