@@ -41,8 +41,9 @@ WORKLOADS = {
     # the other two mechanisms (not the headline metric; same JSON contract, their own units)
     "cfg3": dict(kind="sr", nmol=512, frames=100_000, seed=3,
                  name="cfg3: spin-rotation, 512 CH4 x 1e5 frames (angular momenta + 3 ACFs per molecule + rate)"),
-    "cfg4": dict(kind="qr", nuclei=8192, frames=65_536, seed=4,
-                 name="cfg4 shape: quadrupolar, 8192 nuclei per GPU x 65536 frames x 6 EFG components (5 ACFs + rates)"),
+    "cfg4": dict(kind="qr", nuclei=12_500, frames=65_536, seed=4,
+                 name="cfg4: quadrupolar, 1e5 nuclei over 8 GPUs = 12500 nuclei per GPU x 65536 frames x 6 EFG components "
+                      "(5 ACFs + rates)"),
 }
 
 
@@ -162,9 +163,98 @@ def reference_arm(args, wl):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "pair-frames/s", "cores": len(shards), "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "reference_shim_recorded": shim_record("dd")},
             "e2e": {"value": value, "unit": "pair-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def shim_record(kind):
+    """What oracle/time_reference.py measured in the build container (the GPU box has no /root/reference):
+    the unmodified reference through the pandas shim and the numpy port on the same inputs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cpu_reference_shim.json")) as fh:
+            c = json.load(fh)["cases"][kind]
+        return {"case": c["case"], "reference_units_per_s": c["reference_shim_units_per_s"], "reference_cores": c["reference_cores"],
+                "port_units_per_s_same_inputs": c["port_units_per_s"], "port_over_reference": c["port_over_reference"],
+                "where": "build container, 8 vCPU (profiles/r02_cpu_reference_shim.json)"}
+    except Exception:
+        return None
+
+
+def _ref_qr_worker(job):
+    """Quadrupolar port on a block of nuclei: R_2m from the EFG components, five zero-padded fft/ifft ACFs each
+    (qrax.py:115-166), summed."""
+    from oracle import oracle_np as orc
+    efg = _REF_SHARED["efg"]
+    lo, hi = job
+    acc = None
+    for n in range(lo, hi):
+        V = {k: efg[n, c] for c, k in enumerate(("Vxx", "Vyy", "Vzz", "Vxy", "Vxz", "Vyz"))}
+        ac = np.stack([orc.wiener_khinchin(r) for r in orc.qr_spatial(V)])
+        acc = ac if acc is None else acc + ac
+    return acc
+
+
+def _ref_sr_worker(job):
+    """Spin-rotation port on a small methane box of its own (sr_pipeline: pair table, molecules, SR_func1 per
+    molecule-frame, three ACFs per molecule, mean, rate; SRparse.py:25-262)."""
+    from dynpy_b200 import synth
+    from oracle import oracle_np as orc
+    seed, nmol, F = job
+    box = synth.methane_box(nmol, seed=seed)
+    pos = box.frames(0, F + 1).numpy().transpose(2, 0, 1)
+    out = orc.sr_pipeline(pos, box.symbols, np.arange(1, F + 2), box.celldm, 0.001, "methane", nmol,
+                          [16.495, 16.495, -1.875])
+    return out["rate"]
+
+
+def reference_arm_other(args, wl):
+    """--impl reference for the quadrupolar / spin-rotation workloads: the numpy port on all host cores, each step
+    a bounded sample of the workload's shape (cfg4: cores x 16 nuclei x 65536 frames; cfg3: cores x 8 CH4 x 500
+    frames — the port's pair table is O(A^2) per frame, so the sample keeps the box small)."""
+    import multiprocessing as mp
+
+    from dynpy_b200 import synth
+    from oracle import oracle_np as orc
+    cores = os.cpu_count() or 1
+    if wl["kind"] == "qr":
+        F = wl["frames"]
+        per_core = 16
+        S = cores * per_core
+        _REF_SHARED["efg"] = synth.efg_series(S, F, seed=wl["seed"]).numpy()
+        jobs = [(k * per_core, (k + 1) * per_core) for k in range(cores)]
+        worker, units, unit = _ref_qr_worker, float(S) * F, "nucleus-frames/s"
+        metric = "nucleus-frames/s (quadrupolar ACFs + rates)"
+        sample = "%d nuclei x %d frames per step (of %s)" % (S, F, wl["name"])
+        kind = "qr"
+    else:
+        nmol, F = 8, 500
+        jobs = [(wl["seed"] + k, nmol, F) for k in range(cores)]
+        worker, units, unit = _ref_sr_worker, float(cores * nmol) * F, "molecule-frames/s"
+        metric = "molecule-frames/s (spin-rotation ACFs + rate)"
+        sample = "%d boxes of %d CH4 x %d frames per step (of %s)" % (cores, nmol, F, wl["name"])
+        kind = "sr"
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            parts = pool.map(worker, jobs)
+            if kind == "qr":
+                f = sum(parts) / S
+                orc.qr_from_acf(np.arange(F) * 0.029, f, "127I")
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = units / (ms * 1e-3)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if kind == "qr" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                             "reference_shim_recorded": shim_record(kind)},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -189,7 +279,8 @@ def cpu_baseline_sample(box, wl, F, budget_s=20.0):
             break
     dt = time.perf_counter() - t0
     return {"value": done * F / dt, "unit": "pair-frames/s", "cores": 1, "kind": "port",
-            "sample": "%d pairs x %d frames of the workload, numpy restatement of the reference path, 1 core" % (done, F)}
+            "sample": "%d pairs x %d frames of the workload, numpy restatement of the reference path, 1 core" % (done, F),
+            "reference_shim_recorded": shim_record("dd")}
 
 
 def check_result(ops, dist, wrapped, pi, pj, cell, F, M, G_all, nspins, lo, hi, rank):
@@ -488,16 +579,25 @@ def other_arm(args, wl):
     F = wl["frames"] if args.frames is None else args.frames
     if wl["kind"] == "qr":
         S = wl["nuclei"]  # per GPU: weak scaling, every rank owns its own nuclei (cfg4 shards 1e5 nuclei over 8 GPUs)
-        base = synth.efg_series(256, F, seed=wl["seed"] + rank, device=dev)
-        data = base.repeat(S // 256, 1, 1).contiguous()
+        if args.nuclei:
+            S = args.nuclei
+        base = synth.efg_series(250, F, seed=wl["seed"] + rank, device=dev)
+        data = base.repeat((S + 249) // 250, 1, 1)[:S].contiguous()
         data += 1e-3 * torch.randn_like(data)
         units_rank, unit, alg_bytes, scaling = float(S) * F, "nucleus-frames/s", 48.0, "weak"
         tdev = torch.arange(F, device=dev, dtype=torch.float64) * 0.029
         M = ops.fft_length(F)
 
-        def step(src):
+        nchunk = max(1, min(16, S // 256))
+        cuts = [(S * k) // nchunk for k in range(nchunk + 1)]
+
+        def step(src, ready=None):
+            # `ready`: one event per chunk of nuclei (end-to-end leg: the chunk's host->device copy on the copy stream)
             spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
-            ops.qr_efg_to_spectrum(src, M=M, spectrum=spec)
+            for k in range(nchunk):
+                if ready is not None:
+                    torch.cuda.current_stream().wait_event(ready[k])
+                ops.qr_efg_to_spectrum(src[cuts[k]:cuts[k + 1]], M=M, spectrum=spec)
             dist.allreduce_sum_(spec)
             acf = ops.ifft_acf(spec, F, 1.0 / (float(M) * F * S * world))[[2, 1, 0, 1, 2]].contiguous()
             g, giso = qrax.spectral_dens(tdev, acf, "cartwright")
@@ -516,12 +616,19 @@ def other_arm(args, wl):
         tdev = torch.arange(1, F + 1, device=dev, dtype=torch.float64) * 0.001
         M = ops.fft_length(F)
 
-        def step(src):
-            J, _, _ = ops.sr_angmom(src, mol_atoms[lo:hi].contiguous(), mass, axis_atoms[lo:hi].contiguous(), 0, (L, L, L),
-                                    1000.0, want_omega=False, want_axes=False)
+        nchunk = max(1, min(8, (hi - lo) // 16))
+        cuts = [lo + ((hi - lo) * k) // nchunk // 2 * 2 for k in range(nchunk)] + [hi]   # even blocks: real-pair packing
+
+        def step(src, ready=None):
             spec = torch.zeros((3, M), dtype=torch.float64, device=dev)
-            for c in range(3):
-                ops.wk_acf_sum(J[:, c, :], pack_real_pairs=True, M=M, spectrum=spec[c])
+            for k in range(nchunk):
+                if ready is not None:
+                    torch.cuda.current_stream().wait_event(ready[k])
+                a, b = cuts[k], cuts[k + 1]
+                J, _, _ = ops.sr_angmom(src, mol_atoms[a:b].contiguous(), mass, axis_atoms[a:b].contiguous(), 0, (L, L, L),
+                                        1000.0, want_omega=False, want_axes=False)
+                for c in range(3):
+                    ops.wk_acf_sum(J[:, c, :], pack_real_pairs=True, M=M, spectrum=spec[c])
             dist.allreduce_sum_(spec)
             acf = ops.ifft_acf(spec, F, 1.0 / (float(M) * F * nmol))
             return acf, ops.simpson(acf, tdev, "cartwright").cpu()
@@ -552,14 +659,36 @@ def other_arm(args, wl):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_step, _ = timed(lambda: step(data), args.steps)
     clocks = sampler.stop() if sampler else None
-    host = torch.empty(data.shape, dtype=torch.float64, pin_memory=True)
-    host.copy_(data)
+    # ---- end to end: the rank's inputs start in pinned host memory; they are copied chunk by chunk on a second
+    #      stream while the chunks already on the device are transformed (the copy is the longer leg: PCIe)
+    if wl["kind"] == "qr":
+        rows = [(cuts[k], cuts[k + 1]) for k in range(nchunk)]          # nuclei of chunk k
+    else:
+        rows = [(5 * cuts[k], 5 * cuts[k + 1]) for k in range(nchunk)]  # atoms of the molecules of chunk k
+    import psutil
+    ring = data.numel() * 8 * world > 0.4 * psutil.virtual_memory().available   # all ranks pin host memory on one box
+    if ring:   # not enough host memory to pin every rank's full input: one pinned chunk, re-sent for every chunk
+        big = max(b - a for a, b in rows)
+        host = torch.empty((big,) + tuple(data.shape[1:]), dtype=torch.float64, pin_memory=True)
+        host.copy_(data[:big])
+    else:
+        host = torch.empty(data.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(data)
     staging = torch.empty_like(data)
     host_out = torch.empty((5 if wl["kind"] == "qr" else 3, F), dtype=torch.float64, pin_memory=True)
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_bytes = sum((b - a) for a, b in rows) * int(data[0].numel()) * 8
 
     def e2e_step():
-        staging.copy_(host, non_blocking=True)
-        acf, r = step(staging)
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the previous step has consumed the staging buffer
+        ready = []
+        with torch.cuda.stream(copy_stream):
+            for a, b in rows:
+                staging[a:b].copy_(host[:b - a] if ring else host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
+        acf, r = step(staging, ready)
         host_out.copy_(acf, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return r
@@ -580,7 +709,9 @@ def other_arm(args, wl):
                        "l2": "inputs larger than L2 (%.2f GB per rank); no flush" % (data.numel() * 8 / 1e9)},
             "clocks": clocks,
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(data.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8)},
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(host_out.numel() * 8),
+                    "overlap": "%d chunks copied on a second stream while earlier chunks are transformed" % nchunk,
+                    "host_buffer": "one pinned chunk re-sent per chunk (host memory)" if ring else "full input pinned"},
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg_bytes * units_rank / (ms_step * 1e-3) / 1e9,
                          "peak": hbm, "unit": "GB/s", "frac": alg_bytes * units_rank / (ms_step * 1e-3) / 1e9 / hbm,
                          "traffic": None, "peak_source": how, "algorithmic_bytes_per_unit": alg_bytes}}
@@ -599,6 +730,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=None, help="override the frame count (debug)")
     ap.add_argument("--pairs", type=int, default=None, help="use only the first PAIRS pairs (debug)")
+    ap.add_argument("--nuclei", type=int, default=None, help="quadrupolar workload: nuclei per GPU (default 12500)")
     ap.add_argument("--ws-gb", type=float, default=4.0, help="workspace budget of the fused dipolar call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle / Parseval gate (debug)")
@@ -610,8 +742,7 @@ def main():
     if wl.get("kind") in ("qr", "sr"):
         if args.impl == "reference":
             if int(os.environ.get("RANK", "0")) == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for the dipolar "
-                                  "workloads (the headline metric) only"}))
+                reference_arm_other(args, wl)
             return
         other_arm(args, wl)
     elif args.impl == "reference":

@@ -11,7 +11,7 @@ import pandas as pd
 import torch
 
 from . import ddrax, dist, ops, parseMD, topology
-from .config import default_simpson_mode
+from .config import default_simpson_mode, dump_stages, stage
 from .helper import which_trajs
 
 
@@ -72,26 +72,31 @@ def dd_trajectory(tr, PD, DD, pair_type, analyte_label, analyte_species, simpson
     except AttributeError:
         dmax = 15
     cell = (float(PD.celldm),) * 3
-    wrapped = ops.wrap(tr.pos, cell[0])
-    ft, _ = topology.build_topology(wrapped, tr.symbols, cell, dmax, bond_extra=0.45, dynamic=True)
-    ft.base.classify_exact(DD.identifier)  # raises like Molecule.classify when the formula is absent
-    nat_per_mol = topology.atoms_per_formula(DD.identifier)
-    pi, pj, changing = select_pairs_dynamic(tr.symbols, ft, nat_per_mol, pair_type, analyte_label)
-    dev = wrapped.device
-    if changing is not None:
-        changing = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in changing)
-    G, hit, n_spins, info = ddrax.pair_acf_sum(wrapped, torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev),
-                                               cell, dmax, masked=changing)
+    with stage("wrap + bonds/molecules of every frame (DD-1, DD-3)"):
+        wrapped = ops.wrap(tr.pos, cell[0])
+        ft, _ = topology.build_topology(wrapped, tr.symbols, cell, dmax, bond_extra=0.45, dynamic=True)
+        ft.base.classify_exact(DD.identifier)  # raises like Molecule.classify when the formula is absent
+    with stage("pair selection (DD-3)"):
+        nat_per_mol = topology.atoms_per_formula(DD.identifier)
+        pi, pj, changing = select_pairs_dynamic(tr.symbols, ft, nat_per_mol, pair_type, analyte_label)
+        dev = wrapped.device
+        if changing is not None:
+            changing = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in changing)
+        pi_d, pj_d = torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev)
+    with stage("pair vectors, Y2m words, transforms, sum over pairs (DD-2, DD-4..6)"):
+        G, hit, n_spins, info = ddrax.pair_acf_sum(wrapped, pi_d, pj_d, cell, dmax, masked=changing)
     if n_spins == 0:
         raise ValueError("no pair of the requested kind is ever inside rmax=%r" % (dmax,))
-    G = (G[:, hit] * (2.0 / n_spins)).contiguous()
-    tdev = (torch.from_numpy(tr.frames).to(dev)[hit].to(torch.float64) * float(PD.timestep)).contiguous()
-    EN = ddrax.spec_dens_extr_narr(tdev, G, simpson_mode)
-    rax, tc, F = ddrax.dipolar(EN, symbol1=analyte_species, symbol2='1H')
-    acf_avg = pd.DataFrame({'time': tdev.cpu().numpy()})
-    Gh = G.cpu().numpy()
-    for c, name in enumerate(ddrax.G_COLUMNS):
-        acf_avg[name] = Gh[c]
+    with stage("Simpson + rates (DD-7)"):
+        G = (G[:, hit] * (2.0 / n_spins)).contiguous()
+        tdev = (torch.from_numpy(tr.frames).to(dev)[hit].to(torch.float64) * float(PD.timestep)).contiguous()
+        EN = ddrax.spec_dens_extr_narr(tdev, G, simpson_mode)
+        rax, tc, F = ddrax.dipolar(EN, symbol1=analyte_species, symbol2='1H')
+    with stage("G(tau) to host table"):
+        acf_avg = pd.DataFrame({'time': tdev.cpu().numpy()})
+        Gh = G.cpu().numpy()
+        for c, name in enumerate(ddrax.G_COLUMNS):
+            acf_avg[name] = Gh[c]
     return acf_avg, rax, tc, F, info
 
 
@@ -131,7 +136,8 @@ def DD_module_main(PD, DD):
     res = {}
     for t, traj in enumerate(PD.trajs):
         inner_start_time = time.time()
-        tr = parseMD.PARSE_MD(PD, traj)
+        with stage("trajectory text -> device [A][3][F] (parse + H2D + transpose)"):
+            tr = parseMD.PARSE_MD(PD, traj)
         say("computing two-atom distances...")
         say("computing dipolar quantities...")
         say("computing TCFs...")
@@ -139,7 +145,8 @@ def DD_module_main(PD, DD):
         torch.cuda.synchronize()
         say("--- {t:.2f} seconds ---".format(t=time.time() - inner_start_time))
         if rank == 0:
-            acf_avg.to_csv(PD.traj_dir + traj + '/avg-acf.csv')
+            with stage("avg-acf.csv"):
+                acf_avg.to_csv(PD.traj_dir + traj + '/avg-acf.csv')
         say("1/T1/nH = {r:.3e} Hz, tau_c = {t:.3e} ps, <F(0)^2> = {f:.3e} au^-6".format(r=rax, t=tc, f=F))
         say("For intramolecular contrib. in heteronuclear systems (e.g. C--H relaxation of 13C), multiply 1/T1/nH "
               "by number of bonded spins to obtain 1/T1. E.g. for C-13 in methyl group, nH=3")
@@ -148,4 +155,6 @@ def DD_module_main(PD, DD):
     res_df.columns = ["1/T1/nH", "tau_c", "<F(0)^2>"]
     if rank == 0:
         res_df.to_csv(PD.traj_dir + 'DD-results.csv')
+        dump_stages({"total_s": time.time() - outer_start_time, "pairs": info["pairs"], "frames": int(tr.nframes),
+                     "atoms": int(tr.nat), "full": info["full"], "partial": info["partial"]})
     return res_df

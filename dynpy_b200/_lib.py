@@ -44,6 +44,7 @@ SIGNATURES = {
     "dynpy_dd_ragged_workspace_bytes": (i64, [i64, i64, i64]),
     "dynpy_dd_pairs_ragged_to_acf_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, i64, p, i64, p]),
     "dynpy_dd_pairs_masked_to_acf_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, p, p, p, i64, p, i64, p]),
+    "dynpy_dd_pairs_ragged_capped_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, p, p, p, i64, i64, p, i64, p]),
     "dynpy_sr_angmom_f64": (i32, [p, p, i64, i64, p, i64, i32, p, p, i32, f64, f64, f64, f64, p, p, p, p]),
     "dynpy_simpson_f64": (i32, [p, p, i64, i32, i64, i32, p, p]),
     "dynpy_dft_workspace_bytes": (i64, [i64]),

@@ -576,8 +576,21 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
                                      double rmax, const uint8_t* mask, double* G, int64_t* pair_frames,
                                      int32_t* frame_hit, int64_t M, void* ws, int64_t ws_bytes,
                                      dynpy_stream_t stream) {
+    return dynpy_dd_pairs_ragged_capped_f64(coords, n_atoms, n_frames, pair_i, pair_j, n_pairs, a, b, c, rmax, mask, G,
+                                            pair_frames, frame_hit, n_frames, M, ws, ws_bytes, stream);
+}
+
+int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                                     const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
+                                     double rmax, const uint8_t* mask, double* G, int64_t* pair_frames,
+                                     int32_t* frame_hit, int64_t n_cap, int64_t M, void* ws, int64_t ws_bytes,
+                                     dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = check_M(M, n_frames);
+    if (n_cap < 1 || n_cap > n_frames) {
+        set_error("dynpy_dd_pairs_ragged_capped_f64: n_cap must lie in [1, n_frames]");
+        return DYNPY_ERR_INVALID;
+    }
+    int rc = check_M(M, n_cap);
     if (rc) return rc;
     if (!coords || !pair_i || !pair_j || !G || n_pairs < 0 || n_atoms < 1 || !ws) {
         set_error("dynpy_dd_pairs_ragged_to_acf_f64: invalid arguments");
@@ -587,12 +600,12 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
     DeviceState* d;
     rc = get_device_state(&d, st);
     if (rc) return rc;
-    const i64 N = n_frames;
+    const i64 N = n_frames, NC = n_cap;
     const i64 tbytes = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;
-    i64 cap = (ws_bytes - tbytes - 4096) / dd_ragged_pair_bytes(N, M);
+    i64 cap = (ws_bytes - tbytes - 4096) / dd_ragged_pair_bytes(NC, M);
     if (cap < 1) {
         set_error("dynpy_dd_pairs_ragged_to_acf_f64: workspace too small (need >= %lld bytes)",
-                  (long long)dynpy_dd_ragged_workspace_bytes(N, M, 1));
+                  (long long)dynpy_dd_ragged_workspace_bytes(NC, M, 1));
         return DYNPY_ERR_WORKSPACE;
     }
     if (cap > n_pairs) cap = n_pairs;
@@ -602,29 +615,29 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
     i64* lens = (i64*)carve(cap * 7 * 8);
     double* scale = (double*)carve(cap * 7 * 8);
     double* bias = (double*)carve(cap * 16);
-    int* fidx = (int*)carve(cap * N * 4);
-    double* W = (double*)carve(cap * 14 * N * 8);
+    int* fidx = (int*)carve(cap * NC * 4);
+    double* W = (double*)carve(cap * 14 * NC * 8);
     double* P = (double*)carve(cap * 7 * M * 8);
     double* Pn = M > DYNPY_ROW_LEN ? (double*)carve(cap * 7 * M * 8) : nullptr;
-    double* acf = (double*)carve(cap * 7 * N * 8);
+    double* acf = (double*)carve(cap * 7 * NC * 8);
     cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
     const i64 T_cap = tbytes ? 14 : 0;
 
     for (i64 p0 = 0; p0 < n_pairs; p0 += cap) {
         const i64 cnt = n_pairs - p0 < cap ? n_pairs - p0 : cap;
-        DYNPY_CHECK(launch_dd_ragged_words(coords, N, pair_i, pair_j, p0, cnt, a, b, c, rmax, W, fidx, lens, scale,
+        DYNPY_CHECK(launch_dd_ragged_words(coords, N, NC, pair_i, pair_j, p0, cnt, a, b, c, rmax, W, fidx, lens, scale,
                                            bias, mask, st), "dd ragged words");
-        DYNPY_CHECK(launch_dd_ragged_presence(fidx, lens, N, cnt, pair_frames ? (i64*)pair_frames + p0 : nullptr,
+        DYNPY_CHECK(launch_dd_ragged_presence(fidx, lens, NC, cnt, pair_frames ? (i64*)pair_frames + p0 : nullptr,
                                               frame_hit, st), "dd ragged presence");
         PlanarLoader ld;
         memset(&ld, 0, sizeof(ld));
         ld.re = W;
-        ld.im = W + N;
-        ld.hi = 14 * N;
-        ld.lo = 2 * N;
+        ld.im = W + NC;
+        ld.hi = 14 * NC;
+        ld.lo = 2 * NC;
         ld.n_im_valid = (i64)1 << 62;
         ld.nslots = 7;
-        ld.N = N;
+        ld.N = NC;
         ld.lens = lens;
         ld.bias = bias;
         ld.bias_slot = 3;
@@ -649,10 +662,10 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
         e2.out = acf;
         e2.M = M;
         e2.nslots = 1;
-        e2.n_out = N;
+        e2.n_out = NC;
         e2.scale = 1.0 / (double)M;
         DYNPY_CHECK(forward_spectrum_real(sl, e2, cnt * 7, M, 1, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged inverse");
-        DYNPY_CHECK(launch_dd_ragged_scatter(acf, fidx, lens, N, cnt * 7, G, st), "dd ragged scatter");
+        DYNPY_CHECK(launch_dd_ragged_scatter(acf, fidx, lens, N, NC, cnt * 7, G, st), "dd ragged scatter");
     }
     return DYNPY_OK;
 }

@@ -28,12 +28,12 @@ cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const in
 cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
                                   unsigned long long* out, i64* events, i64 cap, cudaStream_t st);
-cudaError_t launch_dd_ragged_words(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 npairs,
+cudaError_t launch_dd_ragged_words(const double* X, i64 N, i64 NC, const int* pi, const int* pj, i64 pair0, i64 npairs,
                                    double a, double b, double c, double rmax, double* W, int* fidx, i64* lens,
                                    double* scale, double* bias, const unsigned char* mask, cudaStream_t st);
 cudaError_t launch_dd_ragged_presence(const int* fidx, const i64* lens, i64 N, i64 npairs, i64* pair_frames,
                                       int* frame_hit, cudaStream_t st);
-cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 nfft,
+cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 NC, i64 nfft,
                                      double* G, cudaStream_t st);
 cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const int* mol_atoms, i64 n_mol, int nat,
                              const double* mass, const int* axis_atoms, int axis_rule, double a, double b, double c,

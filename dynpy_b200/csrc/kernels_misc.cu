@@ -429,7 +429,7 @@ cudaError_t launch_cart_to_dipolar(const double* dx, const double* dy, const dou
 // complex series of length N_p (Y20, Y21, Y22, r^-3, F20, F21, F22; real ones with zero
 // imaginary plane) and record rank -> frame.  W[pair][7][2][N], fidx[pair][N], lens[7*pair+s].
 __global__ void __launch_bounds__(256)
-k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
+k_dd_ragged_words(const double* __restrict__ X, i64 N, i64 NC, const int* __restrict__ pi, const int* __restrict__ pj,
                   i64 pair0, double a, double b, double c, double rmax2, double* __restrict__ W,
                   int* __restrict__ fidx, i64* __restrict__ lens, double* __restrict__ scale,
                   double* __restrict__ bias, const unsigned char* __restrict__ mask) {
@@ -443,8 +443,8 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
     const i64 p = pair0 + pl;
     const double* xi = X + (i64)pi[p] * 3 * N;
     const double* xj = X + (i64)pj[p] * 3 * N;
-    double* w = W + pl * 14 * N;
-    int* fi = fidx + pl * N;
+    double* w = W + pl * 14 * NC;   // NC = capacity of a compressed series (<= N): pairs of one length class
+    int* fi = fidx + pl * NC;
     double rsum = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
@@ -485,17 +485,17 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
                 tot += cq;
                 if (q < warp) mine += cq;
             }
-            if (ok[e]) {
-                const i64 o = off + mine + __popc(ball[e] & below);
+            const i64 o = off + mine + __popc(ball[e] & below);
+            if (ok[e] && o < NC) {
                 const DDWords d = dd_words(dx[e], dy[e], dz[e], r2[e]);
                 fi[o] = (int)(n0 + e * 256 + threadIdx.x);
-                w[0 * N + o] = d.y20;  w[1 * N + o] = 0.0;
-                w[2 * N + o] = d.y21r; w[3 * N + o] = d.y21i;
-                w[4 * N + o] = d.y22r; w[5 * N + o] = d.y22i;
-                w[6 * N + o] = d.r3;   w[7 * N + o] = 0.0;
-                w[8 * N + o] = d.f20;  w[9 * N + o] = 0.0;
-                w[10 * N + o] = d.f21r; w[11 * N + o] = d.f21i;
-                w[12 * N + o] = d.f22r; w[13 * N + o] = d.f22i;
+                w[0 * NC + o] = d.y20;  w[1 * NC + o] = 0.0;
+                w[2 * NC + o] = d.y21r; w[3 * NC + o] = d.y21i;
+                w[4 * NC + o] = d.y22r; w[5 * NC + o] = d.y22i;
+                w[6 * NC + o] = d.r3;   w[7 * NC + o] = 0.0;
+                w[8 * NC + o] = d.f20;  w[9 * NC + o] = 0.0;
+                w[10 * NC + o] = d.f21r; w[11 * NC + o] = d.f21i;
+                w[12 * NC + o] = d.f22r; w[13 * NC + o] = d.f22i;
                 rsum += d.r3;
             }
             off += tot;
@@ -504,7 +504,7 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
     }
     const double t = block_sum_256(rsum, sh);
     if (threadIdx.x == 0) {
-        const i64 np = base;
+        const i64 np = base < NC ? base : NC;   // a pair longer than the class capacity is a caller error: truncated
         for (int s = 0; s < 7; ++s) {
             lens[pl * 7 + s] = np;
             scale[pl * 7 + s] = 1.0;
@@ -513,11 +513,11 @@ k_dd_ragged_words(const double* __restrict__ X, i64 N, const int* __restrict__ p
         bias[2 * pl + 1] = 0.0;
     }
 }
-cudaError_t launch_dd_ragged_words(const double* X, i64 N, const int* pi, const int* pj, i64 pair0, i64 npairs,
+cudaError_t launch_dd_ragged_words(const double* X, i64 N, i64 NC, const int* pi, const int* pj, i64 pair0, i64 npairs,
                                    double a, double b, double c, double rmax, double* W, int* fidx, i64* lens,
                                    double* scale, double* bias, const unsigned char* mask, cudaStream_t st) {
     if (npairs <= 0) return cudaSuccess;
-    k_dd_ragged_words<<<(unsigned)npairs, 256, 0, st>>>(X, N, pi, pj, pair0, a, b, c, rmax * rmax, W, fidx, lens,
+    k_dd_ragged_words<<<(unsigned)npairs, 256, 0, st>>>(X, N, NC, pi, pj, pair0, a, b, c, rmax * rmax, W, fidx, lens,
                                                         scale, bias, mask);
     return cudaGetLastError();
 }
@@ -541,7 +541,7 @@ cudaError_t launch_dd_ragged_presence(const int* fidx, const i64* lens, i64 N, i
 // G[acc][fidx[pair][k]] += acf[f][k] / (M * N_p^... ) : scatter of per-pair ACFs to frame bins
 // acf holds Re(FFT(P_f))[k] * (1/M) for k < N (n_out = N); f = pair*7 + acc.
 __global__ void k_dd_ragged_scatter(const double* __restrict__ acf, const int* __restrict__ fidx,
-                                    const i64* __restrict__ lens, i64 N, i64 nfft, double* __restrict__ G) {
+                                    const i64* __restrict__ lens, i64 N, i64 NC, i64 nfft, double* __restrict__ G) {
     // series f on gridDim.x (limit 2^31 - 1; gridDim.y stops at 65535 = 9362 pairs), frame chunks on gridDim.y
     const i64 f = blockIdx.x;
     const i64 pl = f / 7;
@@ -550,18 +550,18 @@ __global__ void k_dd_ragged_scatter(const double* __restrict__ acf, const int* _
     if (np <= 0) return;
     const double inv = 1.0 / (double)np;
     for (i64 k = (i64)blockIdx.y * blockDim.x + threadIdx.x; k < np; k += (i64)gridDim.y * blockDim.x)
-        atomicAdd(G + (i64)acc * N + fidx[pl * N + k], acf[f * N + k] * inv);
+        atomicAdd(G + (i64)acc * N + fidx[pl * NC + k], acf[f * NC + k] * inv);   // N frames per G row, NC per series
 }
-cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 nfft,
+cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 NC, i64 nfft,
                                      double* G, cudaStream_t st) {
     if (nfft <= 0) return cudaSuccess;
     const i64 chunk = (i64)7 << 26;   // whole pairs per launch, far below the gridDim.x limit
     for (i64 f0 = 0; f0 < nfft; f0 += chunk) {
         i64 cnt = nfft - f0 < chunk ? nfft - f0 : chunk;
-        int gy = (int)((N + 255) / 256);
+        int gy = (int)((NC + 255) / 256);
         if (gy > 64) gy = 64;
         dim3 grid((unsigned)cnt, gy);
-        k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf + f0 * N, fidx + (f0 / 7) * N, lens + f0, N, cnt, G);
+        k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf + f0 * NC, fidx + (f0 / 7) * NC, lens + f0, N, NC, cnt, G);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -79,6 +79,7 @@ def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True, masked=None):
             part = (counts > 0) & ~full
             full_i, full_j = pi[full].contiguous(), pj[full].contiguous()
             part_i, part_j = pi[part].contiguous(), pj[part].contiguous()
+            part_counts = counts[part].contiguous()
             info["full"] = int(full.sum())
             info["partial"] = int(part.sum())
             info["absent"] = (hi - lo) - info["full"] - info["partial"]
@@ -88,7 +89,7 @@ def pair_acf_sum(wrapped, pair_i, pair_j, cell, rmax, shard=True, masked=None):
             label_used[full_i.long()] = 1
             label_used[full_j.long()] = 1
         if part_i is not None and part_i.numel():
-            ops.dd_pairs_ragged_to_acf(wrapped, part_i, part_j, cell, rmax, M=M, G=G)
+            ops.dd_pairs_ragged_to_acf(wrapped, part_i, part_j, cell, rmax, M=M, G=G, counts=part_counts)
             label_used[part_i.long()] = 1
             label_used[part_j.long()] = 1
     if masked is not None and masked[0].numel() and (not shard or dist.rank_world()[0] == 0):

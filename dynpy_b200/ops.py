@@ -317,16 +317,18 @@ def dd_pairs_to_spectrum(coords, pair_i, pair_j, cell, M=None, spectrum=None, ws
 
 
 def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, ws_budget: int = 8 << 30, mask=None,
-                           pair_frames=None, frame_hit=None):
+                           pair_frames=None, frame_hit=None, counts=None):
     """Ragged dipolar path: G[7, F] += per-pair ACFs binned at the k-th present frame.  Optional mask [P, F]
     uint8 (frames in which the pair row passes the molecule filter), pair_frames [P] int64 out (frames present),
-    frame_hit [F] int32 (set to 1 where some pair is present)."""
+    frame_hit [F] int32 (set to 1 where some pair is present).
+    counts [P] int64 (frames each pair is inside rmax, from dd_pair_count): the pairs are then processed by LENGTH
+    CLASS — transform length and buffers sized by the class's largest count instead of F (not with mask /
+    pair_frames, whose rows follow the caller's pair order)."""
     lib = _lib.load()
     coords = _chk(coords, torch.float64, "coords")
     pair_i = _chk(pair_i, torch.int32, "pair_i")
     pair_j = _chk(pair_j, torch.int32, "pair_j")
     A, three, F = coords.shape
-    M = fft_length(F) if M is None else int(M)
     if G is None:
         G = torch.zeros((7, F), dtype=torch.float64, device=coords.device)
     _chk(G, torch.float64, "G")
@@ -338,20 +340,39 @@ def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, w
         pair_frames = _chk(pair_frames, torch.int64, "pair_frames")
     if frame_hit is not None:
         frame_hit = _chk(frame_hit, torch.int32, "frame_hit")
-    one = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 1))
-    two = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, 2))
-    per = two - one
-    n = max(1, min(npairs, (ws_budget - (one - per)) // per))
-    with torch.cuda.device(coords.device):
-        wsb = int(lib.dynpy_dd_ragged_workspace_bytes(F, M, n))
-        ws = workspace(coords.device, wsb)
-        rc = lib.dynpy_dd_pairs_masked_to_acf_f64(coords.data_ptr(), A, F, pair_i.data_ptr(), pair_j.data_ptr(), npairs,
-                                                  float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
-                                                  mask.data_ptr() if mask is not None else None, G.data_ptr(),
-                                                  pair_frames.data_ptr() if pair_frames is not None else None,
-                                                  frame_hit.data_ptr() if frame_hit is not None else None,
-                                                  M, ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "dynpy_dd_pairs_masked_to_acf_f64")
+
+    def run(pi, pj, n_cap, Mc, msk, pf):
+        n = pi.numel()
+        one = int(lib.dynpy_dd_ragged_workspace_bytes(n_cap, Mc, 1))
+        two = int(lib.dynpy_dd_ragged_workspace_bytes(n_cap, Mc, 2))
+        per = two - one
+        nb = max(1, min(n, (ws_budget - (one - per)) // per))
+        with torch.cuda.device(coords.device):
+            wsb = int(lib.dynpy_dd_ragged_workspace_bytes(n_cap, Mc, nb))
+            ws = workspace(coords.device, wsb)
+            rc = lib.dynpy_dd_pairs_ragged_capped_f64(coords.data_ptr(), A, F, pi.data_ptr(), pj.data_ptr(), n,
+                                                      float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
+                                                      msk.data_ptr() if msk is not None else None, G.data_ptr(),
+                                                      pf.data_ptr() if pf is not None else None,
+                                                      frame_hit.data_ptr() if frame_hit is not None else None,
+                                                      int(n_cap), int(Mc), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "dynpy_dd_pairs_ragged_capped_f64")
+
+    import os
+    if (counts is None or mask is not None or pair_frames is not None or npairs == 0
+            or os.environ.get("DYNPY_RAGGED_CLASSES") == "0"):
+        run(pair_i, pair_j, F, fft_length(F) if M is None else int(M), mask, pair_frames)
+        return G
+    # ---- length classes: pairs whose count needs the same transform length go together
+    counts = _chk(counts, torch.int64, "counts")
+    assert counts.numel() == npairs
+    ch = counts.cpu().numpy()
+    uniq, inv = np.unique(ch, return_inverse=True)
+    mc = np.array([fft_length(int(c)) if c > 0 else 0 for c in uniq], dtype=np.int64)[inv]
+    for Mc in sorted(set(mc.tolist()) - {0}, reverse=True):
+        sel = torch.from_numpy(np.nonzero(mc == Mc)[0]).to(coords.device)
+        n_cap = int(min(F, ch[mc == Mc].max()))
+        run(pair_i[sel].contiguous(), pair_j[sel].contiguous(), n_cap, Mc, None, None)
     return G
 
 

@@ -189,6 +189,17 @@ int dynpy_dd_pairs_masked_to_acf_f64(const double* coords, int64_t n_atoms, int6
                                      double* G, int64_t* pair_frames, int32_t* frame_hit, int64_t M,
                                      void* ws, int64_t ws_bytes, dynpy_stream_t stream);
 
+/* The same call for pairs of one LENGTH CLASS: every pair of the call is present in at most n_cap frames
+ * (n_cap <= n_frames; the caller knows the counts from dynpy_dd_pair_count_f64), so the compressed series, the
+ * transform length M >= 2 n_cap - 1 and the workspace (dynpy_dd_ragged_workspace_bytes(n_cap, M, pairs)) are sized
+ * by n_cap instead of n_frames: a pair that is inside rmax for 5 % of a long trajectory costs a 5 %-length
+ * transform.  Pairs with more than n_cap present frames are truncated (caller error). */
+int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
+                                     const int32_t* pair_j, int64_t n_pairs, double a, double b, double c,
+                                     double rmax, const uint8_t* mask, double* G, int64_t* pair_frames,
+                                     int32_t* frame_hit, int64_t n_cap, int64_t M, void* ws, int64_t ws_bytes,
+                                     dynpy_stream_t stream);
+
 /* ---- spin-rotation -------------------------------------------------------------------------
  * replaces SR_func1 per (molecule, frame) (SRrax.py:438-510) and the backward-difference
  * velocities (SRparse.py:127-134).  pos is RAW [n_atoms][3][n_frames]; vel may be NULL
