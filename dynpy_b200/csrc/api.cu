@@ -552,7 +552,7 @@ int dynpy_dd_pairs_to_spectrum_f64(const double* coords, int64_t n_atoms, int64_
 static i64 dd_ragged_pair_bytes(i64 N, i64 M) {
     i64 w = align_up(14 * N * 8, 256);        // compressed words
     i64 fi = align_up(N * 4, 256);            // rank -> frame
-    i64 p = align_up(7 * M * 8, 256) * (M > DYNPY_ROW_LEN ? 2 : 1);  // per-series power spectra (+ natural-order copy)
+    i64 p = align_up(7 * M * 8, 256) * 2;     // per-series power spectra + their even parts in natural order
     i64 acf = align_up(7 * N * 8, 256);       // per-series ACFs
     i64 small = 7 * 8 * 2 + 16 + 256;         // lens, scale, bias
     return w + fi + p + acf + small;
@@ -618,7 +618,7 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
     int* fidx = (int*)carve(cap * NC * 4);
     double* W = (double*)carve(cap * 14 * NC * 8);
     double* P = (double*)carve(cap * 7 * M * 8);
-    double* Pn = M > DYNPY_ROW_LEN ? (double*)carve(cap * 7 * M * 8) : nullptr;
+    double* Pn = (double*)carve(cap * 7 * M * 8);
     double* acf = (double*)carve(cap * 7 * NC * 8);
     cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
     const i64 T_cap = tbytes ? 14 : 0;
@@ -647,24 +647,22 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
         ep.M = M;
         ep.nslots = 7;
         DYNPY_CHECK(forward_planar_power(ld, ep, cnt * 7, M, 7, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged forward");
-        SpectrumLoader sl;
-        sl.S = P;
+        // even parts of the 7 spectra of every pair in natural order, two per inverse transform
+        DYNPY_CHECK(launch_spectrum_even_natural(P, Pn, cnt * 7, M, st), "dd ragged even parts");
+        SpectrumPairLoader sl;
+        sl.S = Pn;
         sl.M = M;
-        sl.M1 = M > DYNPY_ROW_LEN ? (int)(M / DYNPY_ROW_LEN) : 1;
-        sl.natural = 0;
-        if (Pn) {
-            DYNPY_CHECK(launch_spectrum_to_natural(P, Pn, cnt * 7, sl.M1, st), "dd ragged transpose");
-            sl.S = Pn;
-            sl.natural = 1;
-        }
+        sl.n_spec = cnt * 7;
         EpiParams e2;
         memset(&e2, 0, sizeof(e2));
         e2.out = acf;
         e2.M = M;
         e2.nslots = 1;
         e2.n_out = NC;
+        e2.n_series = cnt * 7;
         e2.scale = 1.0 / (double)M;
-        DYNPY_CHECK(forward_spectrum_real(sl, e2, cnt * 7, M, 1, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged inverse");
+        DYNPY_CHECK(forward_spectrum_real2(sl, e2, (cnt * 7 + 1) / 2, M, T, T_cap, d->tw4096, d->n_sm, st),
+                    "dd ragged inverse");
         DYNPY_CHECK(launch_dd_ragged_scatter(acf, fidx, lens, N, NC, cnt * 7, G, st), "dd ragged scatter");
     }
     return DYNPY_OK;

@@ -290,6 +290,25 @@ struct SpectrumLoader {
     __device__ __forceinline__ cd finish(const Ctx& c, cd v) const { return v; }
 };
 
+// Two real EVEN spectra per transform, natural frequency order (k_spectrum_to_natural with sym = 1): series
+// P[2f] + i P[2f+1].  The transform of a real even sequence is real, so Re / Im of the result are the two ACFs
+// (EPI_WRITE_REAL2): half the inverse transforms of the per-series path.
+struct SpectrumPairLoader {
+    static constexpr bool DENSE = true;
+    const double* S;   // [n_spec][M]
+    i64 M;
+    i64 n_spec;
+    struct Ctx { const double* a; const double* b; };
+    __device__ __forceinline__ Ctx begin(i64 f) const {
+        Ctx c; c.a = S + 2 * f * M; c.b = (2 * f + 1 < n_spec) ? S + (2 * f + 1) * M : nullptr; return c;
+    }
+    __device__ __forceinline__ cd load(const Ctx& c, i64 n) const {
+        return make_double2(__ldg(c.a + n), c.b ? __ldg(c.b + n) : 0.0);
+    }
+    __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const { return load(c, n); }
+    __device__ __forceinline__ cd finish(const Ctx& c, cd v) const { return v; }
+};
+
 // Row loader for the second pass: T[f_local][k1][n2]
 struct TLoader {
     const cd* T;
@@ -303,13 +322,14 @@ struct TLoader {
 };
 
 // ---------------------------------------------------------------- epilogue parameters
-enum EpiMode { EPI_ACC_POWER = 0, EPI_WRITE_REAL = 1, EPI_WRITE_POWER = 2 };
+enum EpiMode { EPI_ACC_POWER = 0, EPI_WRITE_REAL = 1, EPI_WRITE_POWER = 2, EPI_WRITE_REAL2 = 3 };
 struct EpiParams {
     double* out;        // ACC_POWER: S'[acc][M] ; WRITE_REAL: out[f][n_out] ; WRITE_POWER: P[f][M] (internal order)
     i64 M;              // full transform length
     int nslots;         // ACC_POWER: acc id = 4-bit field (f % nslots) of acc_pack
     unsigned long long acc_pack;
     i64 n_out;          // WRITE_REAL: outputs kept (k < n_out)
+    i64 n_series;       // WRITE_REAL2: out[2f] = Re, out[2f+1] = Im (when 2f+1 < n_series)
     double scale;       // WRITE_REAL: multiplier
 };
 
@@ -405,6 +425,18 @@ k_rows(Loader ld, EpiParams ep, const cd* __restrict__ twp, i64 f_begin, i64 f_e
                 for (int j = 0; j < RL; ++j) {
                     i64 k = (i64)k1row + (i64)M1 * (kk0 + j * kstride);
                     if (k < ep.n_out) ep.out[f * ep.n_out + k] = v[j].x * ep.scale;
+                }
+            }
+        } else if constexpr (MODE == EPI_WRITE_REAL2) {
+            if (active) {
+                const bool two = 2 * f + 1 < ep.n_series;
+#pragma unroll
+                for (int j = 0; j < RL; ++j) {
+                    i64 k = (i64)k1row + (i64)M1 * (kk0 + j * kstride);
+                    if (k < ep.n_out) {
+                        ep.out[2 * f * ep.n_out + k] = v[j].x * ep.scale;
+                        if (two) ep.out[(2 * f + 1) * ep.n_out + k] = v[j].y * ep.scale;
+                    }
                 }
             }
         } else {  // EPI_WRITE_POWER: per-series |X|^2 in internal order

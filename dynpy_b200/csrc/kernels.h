@@ -65,4 +65,8 @@ cudaError_t forward_qr_acc(const QrLoader& ld, const EpiParams& ep, i64 n_fft, i
 cudaError_t forward_spectrum_real(const SpectrumLoader& ld, const EpiParams& ep, i64 n_fft, i64 M, int nslots,
                                   cd* T, i64 T_cap, const cd* tw, int n_sm, cudaStream_t st);
 
+cudaError_t forward_spectrum_real2(const SpectrumPairLoader& ld, const EpiParams& ep, i64 n_fft, i64 M, cd* T,
+                                   i64 T_cap, const cd* tw, int n_sm, cudaStream_t st);
+cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_spec, i64 M, cudaStream_t st);
+
 }  // namespace dynpy

@@ -600,6 +600,58 @@ cudaError_t launch_spectrum_to_natural(const double* in, double* out, i64 n_spec
     return cudaGetLastError();
 }
 
+// Even part of power spectra, natural order: out[f][k] = (P[f][k] + P[f][(M - k) % M]) / 2 with P in the engine's
+// internal order (two-pass lengths: element k = k1 + M1 k2 at [k1][k2]; its mirror is [M1 - k1][4095 - k2], or
+// [0][(4096 - k2) % 4096] for k1 = 0) or already natural (single-pass lengths).  Re FFT(P) = FFT(even part of P):
+// the even parts of two spectra can share one transform (SpectrumPairLoader).
+__global__ void __launch_bounds__(256) k_spectrum_even_natural(const double* __restrict__ in, double* __restrict__ out,
+                                                               int M1) {
+    __shared__ double tile[32][33];
+    const i64 f = blockIdx.z;
+    in += f * (i64)M1 * DYNPY_ROW_LEN;
+    out += f * (i64)M1 * DYNPY_ROW_LEN;
+    const int k2_0 = blockIdx.x * 32, k1_0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + j, k2 = k2_0 + tx;
+        if (k1 < M1) {
+            const int m1 = k1 ? M1 - k1 : 0;
+            const int m2 = k1 ? DYNPY_ROW_LEN - 1 - k2 : (DYNPY_ROW_LEN - k2) & (DYNPY_ROW_LEN - 1);
+            tile[j][tx] = 0.5 * (in[(i64)k1 * DYNPY_ROW_LEN + k2] + in[(i64)m1 * DYNPY_ROW_LEN + m2]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + tx;
+        if (k1 < M1) out[(i64)(k2_0 + j) * M1 + k1] = tile[tx][j];
+    }
+}
+__global__ void k_spectrum_even_single(const double* __restrict__ in, double* __restrict__ out, i64 M, i64 total) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 f = e / M, k = e - f * M;
+        out[e] = 0.5 * (in[e] + in[f * M + (k ? M - k : 0)]);
+    }
+}
+cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_spec, i64 M, cudaStream_t st) {
+    if (n_spec <= 0) return cudaSuccess;
+    if (M <= DYNPY_ROW_LEN) {
+        const i64 total = n_spec * M;
+        i64 blocks = (total + 255) / 256;
+        if (blocks > 65535 * 16) blocks = 65535 * 16;
+        k_spectrum_even_single<<<(unsigned)blocks, 256, 0, st>>>(in, out, M, total);
+        return cudaGetLastError();
+    }
+    const int M1 = (int)(M / DYNPY_ROW_LEN);
+    for (i64 f0 = 0; f0 < n_spec; f0 += 32768) {
+        const i64 cnt = n_spec - f0 < 32768 ? n_spec - f0 : 32768;
+        dim3 grid(DYNPY_ROW_LEN / 32, (unsigned)((M1 + 31) / 32), (unsigned)cnt);
+        k_spectrum_even_natural<<<grid, 256, 0, st>>>(in + f0 * M, out + f0 * M, M1);
+    }
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ spin-rotation
 __device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3], double x[3]) {
     // Gaussian elimination with partial pivoting (what numpy.linalg.solve / LAPACK gesv does)

@@ -76,11 +76,21 @@ def h2d_sharded(host: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     cuts = [(n * r) // world for r in range(world + 1)]
     mine = out[cuts[rank]:cuts[rank + 1]]
     mine.copy_(host[cuts[rank]:cuts[rank + 1]], non_blocking=True)
-    if n % world == 0 and out.is_contiguous():
-        dist.all_gather_into_tensor(out, mine)     # in place: rank r's block is already at its final offset
-    else:
-        dist.all_gather([out[cuts[r]:cuts[r + 1]] for r in range(world)], mine)
+    gather_blocks(out, cuts, mine)
     return out
+
+
+def gather_blocks(full: torch.Tensor, cuts, mine: torch.Tensor) -> None:
+    """Every rank holds block ``full[cuts[rank]:cuts[rank+1]]`` (= mine); afterwards every rank holds all of
+    ``full``.  Equal blocks: ONE in-place all_gather_into_tensor; ragged blocks (the collective needs equal
+    sizes): one broadcast per block."""
+    world = dist.get_world_size()
+    sizes = {cuts[r + 1] - cuts[r] for r in range(world)}
+    if len(sizes) == 1 and full.is_contiguous():
+        dist.all_gather_into_tensor(full, mine)     # in place: rank r's block is already at its final offset
+    else:
+        for r in range(world):
+            dist.broadcast(full[cuts[r]:cuts[r + 1]], src=r)
 
 
 def broadcast_object(obj, src: int = 0):

@@ -137,10 +137,7 @@ def _load_frames(path, nat, header_lines, cols, printed, device, scale_div=0.529
     full = torch.empty((F, nat, 3), dtype=torch.float64, device=device)
     part = full[cuts[rank]:cuts[rank + 1]]
     part.copy_(mine, non_blocking=True)
-    if F % world == 0:
-        tdist.all_gather_into_tensor(full, part)
-    else:
-        tdist.all_gather([full[cuts[r]:cuts[r + 1]] for r in range(world)], part)
+    dist.gather_blocks(full, cuts, part)
     box = [(sym, mine_ids)]
     if header_ids is not None:
         parts = [None] * world

@@ -6,7 +6,8 @@ sys.path.insert(0, '.')
 from dynpy_b200 import DDparse, ops, synth, topology
 nmol = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
-box = synth.water_box(nmol, seed=2).to("cuda")
+import os
+box = synth.water_box(nmol, seed=2, trans_amp=float(os.environ.get("TRANS_AMP", "0.03"))).to("cuda")
 raw = box.trajectory(F, chunk=4096)
 L = box.celldm
 cell = (L, L, L)
@@ -24,3 +25,25 @@ A = raw.shape[0]
 print("atoms %d frames %d: wrap %.2f ms, build_topology %.2f ms (%.3e atom-pair-frames/s), select_pairs %.2f ms, "
       "deviating frames %d, pairs %d" % (A, F, dt_wrap * 1e3, dt_topo * 1e3, A * (A - 1) / 2 * F / dt_topo, dt_sel * 1e3,
                                          len(ft.frames), len(pi)))
+
+# cross-check of the device scan against a brute-force torch evaluation on the first frames
+from dynpy_b200.elements import SYM2COVRAD
+nchk = 256
+sub = w[:, :, :nchk].contiguous()
+two0 = topology.frame_pairs(sub, cell, 0, L)
+b0 = topology.bonded(two0, box.symbols, 0.45)
+expect = torch.zeros((A, A), dtype=torch.uint8)
+expect[torch.from_numpy(two0["i"][b0]), torch.from_numpy(two0["j"][b0])] = 1
+rc = torch.tensor([SYM2COVRAD[s] for s in box.symbols], dtype=torch.float64, device="cuda")
+bad, first = ops.topology_check(sub, rc, 0.45, expect.cuda(), cell, L)
+thr = rc[:, None] + rc[None, :] + 0.45
+iu = torch.triu(torch.ones((A, A), dtype=torch.bool, device="cuda"), 1)
+ref_bad = 0
+for f0 in range(0, nchk, 32):
+    x = sub[:, :, f0:f0 + 32]                                  # [A,3,T]
+    d = x[:, None] - x[None, :]                                 # [A,A,3,T]
+    d = d - L * torch.round(d / L)
+    r = torch.sqrt((d * d).sum(2))                              # [A,A,T]
+    bond = r <= thr[:, :, None]
+    ref_bad += int(((bond != expect.cuda()[:, :, None].bool()) & iu[:, :, None]).sum())
+print("topology_check on %d frames: device %d mismatching pair-frames, torch brute force %d" % (nchk, bad, ref_bad))
