@@ -414,7 +414,7 @@ def native_arm(args, wl):
     tdev = torch.arange(1, F + 1, device=dev, dtype=torch.float64) * 0.001
     M = ops.fft_length(F)
     lo, hi = dist.shard_range(P, rank, world)
-    ws_budget = int(args.ws_gb * (1 << 30))
+    ws_budget = int(args.ws_gb * (1 << 30)) if args.ws_gb else None     # None: the library's adaptive default
 
     present = [float(P) * float(F)]
 
@@ -731,7 +731,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="override the frame count (debug)")
     ap.add_argument("--pairs", type=int, default=None, help="use only the first PAIRS pairs (debug)")
     ap.add_argument("--nuclei", type=int, default=None, help="quadrupolar workload: nuclei per GPU (default 12500)")
-    ap.add_argument("--ws-gb", type=float, default=4.0, help="workspace budget of the fused dipolar call")
+    ap.add_argument("--ws-gb", type=float, default=None,
+                    help="workspace budget of the fused dipolar call in GiB (default: a quarter of the free memory, 4..32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle / Parseval gate (debug)")
     ap.add_argument("--rmax", type=float, default=None,

@@ -47,7 +47,7 @@ def select_pairs_dynamic(symbols, ft, nat_per_mol, pair_type, analyte_label):
     (mi, mj, mask [K, F] uint8) for those that do, mask = frames in which the row is kept."""
     i, j, sel = _eligible(symbols, nat_per_mol, analyte_label)
     base_same = ft.base.mol_rank[i] == ft.base.mol_rank[j]
-    if pair_type not in ('intra', 'inter') or not ft.frames:
+    if pair_type not in ('intra', 'inter') or not ft.changes:
         pi, pj = select_pairs(symbols, ft.base, nat_per_mol, pair_type, analyte_label)
         return pi, pj, None
     want_same = pair_type == 'intra'

@@ -557,10 +557,13 @@ static i64 dd_ragged_pair_bytes(i64 N, i64 M) {
     i64 small = 7 * 8 * 2 + 16 + 256;         // lens, scale, bias
     return w + fi + p + acf + small;
 }
+// one spare row of the packed even spectra and of the ACFs (odd pair counts: see dd_pack_rows)
+static i64 dd_ragged_extra_bytes(i64 N, i64 M) { return align_up(M * 8, 256) + align_up(N * 8, 256); }
+
 int64_t dynpy_dd_ragged_workspace_bytes(int64_t n_frames, int64_t M, int64_t pairs) {
     if (pairs < 1) pairs = 1;
     i64 t = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;  // T for >= 14 transforms in flight
-    return pairs * dd_ragged_pair_bytes(n_frames, M) + t + 4096;
+    return pairs * dd_ragged_pair_bytes(n_frames, M) + t + 4096 + dd_ragged_extra_bytes(n_frames, M);
 }
 
 int dynpy_dd_pairs_ragged_to_acf_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const int32_t* pair_i,
@@ -602,7 +605,7 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
     if (rc) return rc;
     const i64 N = n_frames, NC = n_cap;
     const i64 tbytes = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;
-    i64 cap = (ws_bytes - tbytes - 4096) / dd_ragged_pair_bytes(NC, M);
+    i64 cap = (ws_bytes - tbytes - 4096 - dd_ragged_extra_bytes(NC, M)) / dd_ragged_pair_bytes(NC, M);
     if (cap < 1) {
         set_error("dynpy_dd_pairs_ragged_to_acf_f64: workspace too small (need >= %lld bytes)",
                   (long long)dynpy_dd_ragged_workspace_bytes(NC, M, 1));
@@ -618,8 +621,8 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
     int* fidx = (int*)carve(cap * NC * 4);
     double* W = (double*)carve(cap * 14 * NC * 8);
     double* P = (double*)carve(cap * 7 * M * 8);
-    double* Pn = (double*)carve(cap * 7 * M * 8);
-    double* acf = (double*)carve(cap * 7 * NC * 8);
+    double* Pn = (double*)carve((cap * 7 + 1) * M * 8);
+    double* acf = (double*)carve((cap * 7 + 1) * NC * 8);
     cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
     const i64 T_cap = tbytes ? 14 : 0;
 
@@ -647,21 +650,23 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
         ep.M = M;
         ep.nslots = 7;
         DYNPY_CHECK(forward_planar_power(ld, ep, cnt * 7, M, 7, T, T_cap, d->tw4096, d->n_sm, st), "dd ragged forward");
-        // even parts of the 7 spectra of every pair in natural order, two per inverse transform
+        // even parts of the 7 spectra of every pair in natural order, two per inverse transform; the rows are
+        // permuted (dd_pack_rows) so that the two spectra of a transform have the same magnitude
+        const i64 n_rows = dd_pack_rows(cnt);
         DYNPY_CHECK(launch_spectrum_even_natural(P, Pn, cnt * 7, M, st), "dd ragged even parts");
         SpectrumPairLoader sl;
         sl.S = Pn;
         sl.M = M;
-        sl.n_spec = cnt * 7;
+        sl.n_spec = n_rows;
         EpiParams e2;
         memset(&e2, 0, sizeof(e2));
         e2.out = acf;
         e2.M = M;
         e2.nslots = 1;
         e2.n_out = NC;
-        e2.n_series = cnt * 7;
+        e2.n_series = n_rows;
         e2.scale = 1.0 / (double)M;
-        DYNPY_CHECK(forward_spectrum_real2(sl, e2, (cnt * 7 + 1) / 2, M, T, T_cap, d->tw4096, d->n_sm, st),
+        DYNPY_CHECK(forward_spectrum_real2(sl, e2, n_rows / 2, M, T, T_cap, d->tw4096, d->n_sm, st),
                     "dd ragged inverse");
         DYNPY_CHECK(launch_dd_ragged_scatter(acf, fidx, lens, N, NC, cnt * 7, G, st), "dd ragged scatter");
     }

@@ -42,11 +42,11 @@ static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_
     int gy = (4 * per_sm * n_sm + tiles - 1) / tiles;   // >= 4 waves
     if (gy > p.items) gy = (int)p.items;
     if (gy < 1) gy = 1;
-    static int v3 = -1;
-    if (v3 < 0) { const char* en = getenv("DYNPY_TPC2"); v3 = (en && en[0] == 'o') ? 0 : 1; }   // "old": per-series loads (A/B)
+    const char* en = getenv("DYNPY_TPC2");
+    const int v3 = (en && en[0] == 'o') ? 0 : 1;   // "old": per-series loads (A/B)
     if (v3) {
-        static int per = -1;
-        if (per < 0) { const char* en = getenv("DYNPY_TPC3_PER_SM"); per = en ? atoi(en) : 3; }
+        const char* pe = getenv("DYNPY_TPC3_PER_SM");
+        const int per = pe ? atoi(pe) : 2;   // 2 x 128 threads at 254 registers (no spills) measured faster than 3 x 128 at 168
         const size_t smem3 = smem + (size_t)16 * B * sizeof(cd);
         auto kern = per == 2 ? k_cols_tpc3<B, C, 2> : k_cols_tpc3<B, C, 3>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
@@ -208,9 +208,15 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
             {
                 ProfScope prof(PROF_WORDS, st);
                 // N % 4 == 0: 32-byte loads / stores (every stream is 32-byte aligned then); DYNPY_DD_GEOM=scalar for A/B
-                static int vec = -1;
-                if (vec < 0) { const char* e = getenv("DYNPY_DD_GEOM"); vec = (e && e[0] == 's') ? 0 : 1; }
-                if (vec && (N & 3) == 0 && ((uintptr_t)X & 31) == 0)
+                const char* ge = getenv("DYNPY_DD_GEOM");
+                const int vec = (ge && ge[0] == 's') ? 0 : (ge && ge[0] == 't') ? 2 : 1;
+                if (vec == 2 && (N & 1) == 0 && ((uintptr_t)X & 15) == 0) {
+                    // TMA-staged form (DYNPY_DD_GEOM=tma): bulk copies through a 4-stage shared-memory ring
+                    const size_t smem = (size_t)GEOM_STAGES * 6 * GEOM_TILE * 8 + GEOM_STAGES * 8;
+                    DYNPY_CHECK(cudaFuncSetAttribute(k_dd_geom_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                "dd geometry (tma) attribute");
+                    k_dd_geom_tma<<<2 * n_sm, GEOM_NT, smem, st>>>(gp);
+                } else if (vec && (N & 3) == 0 && ((uintptr_t)X & 31) == 0)
                     k_dd_geom4<<<dim3((unsigned)((N + 2047) / 2048), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
                 else
                     k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);

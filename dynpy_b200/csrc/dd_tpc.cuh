@@ -170,6 +170,138 @@ __global__ void __launch_bounds__(256) k_dd_geom4(const GeomParams p) {
     }
 }
 
+// ---------------------------------------------------------------- TMA-staged form of the geometry kernel
+// The six coordinate streams of a pair are moved by the TMA engine (cp.async.bulk global -> shared, completion
+// counted on an mbarrier) through a ring of GEOM_STAGES tiles of GEOM_TILE frames; no thread issues a load for
+// them, the LSU only sees the conflict-free shared-memory reads and the 32-byte stores of the two output streams.
+// A CTA walks a contiguous range of (pair slot, frame tile) units, so its ring never drains between pairs.
+// Needs N % 2 == 0 (bulk copies move multiples of 16 bytes from 16-byte aligned addresses).
+#define GEOM_TILE 512
+#define GEOM_STAGES 4
+#define GEOM_NT 256
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(GEOM_NT, 2) k_dd_geom_tma(const GeomParams p) {
+    extern __shared__ __align__(128) unsigned char geom_smem[];
+    double* buf = reinterpret_cast<double*>(geom_smem);                       // [STAGES][6][TILE]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(buf + GEOM_STAGES * 6 * GEOM_TILE);
+    __shared__ double sred[GEOM_NT / 32];
+    const i64 tiles = (p.N + GEOM_TILE - 1) / GEOM_TILE;
+    const i64 units = p.n_slots * tiles;
+    const i64 u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    if (u0 >= u1) return;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GEOM_STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // producer (thread 0): the six streams of unit u into stage s
+    auto issue = [&](i64 u, int s) {
+        const i64 slot = u / tiles, tile = u - slot * tiles;
+        const i64 pr = p.pair0 + slot;
+        if (pr >= p.n_pairs) {   // slot beyond the last pair: nothing to copy, complete the phase by a plain arrive
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + s)) : "memory");
+            return;
+        }
+        const i64 f0 = tile * GEOM_TILE;
+        const unsigned bytes = (unsigned)((p.N - f0 < GEOM_TILE ? p.N - f0 : GEOM_TILE) * 8);
+        const double* xi = p.X + (i64)__ldg(p.pi + pr) * 3 * p.N + f0;
+        const double* xj = p.X + (i64)__ldg(p.pj + pr) * 3 * p.N + f0;
+        double* dst = buf + (i64)s * 6 * GEOM_TILE;
+        mbar_expect_tx(full + s, 6 * bytes);
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            tma_load_1d(dst + (2 * ax) * GEOM_TILE, xi + ax * p.N, bytes, full + s);
+            tma_load_1d(dst + (2 * ax + 1) * GEOM_TILE, xj + ax * p.N, bytes, full + s);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < GEOM_STAGES; ++s)
+            if (u0 + s < u1) issue(u0 + s, s);
+    const double L[3] = {p.a, p.b, p.c};
+    double rs = 0.0;
+    i64 cur_slot = u0 / tiles;
+    auto flush = [&](i64 slot) {
+        double t = rs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0 && p.pair0 + slot < p.n_pairs) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < GEOM_NT / 32; ++w) a += sred[w];
+            atomicAdd(p.rsum + slot, a);
+        }
+        __syncthreads();
+        rs = 0.0;
+    };
+    for (i64 u = u0; u < u1; ++u) {
+        const int s = (int)((u - u0) % GEOM_STAGES);
+        const unsigned parity = (unsigned)(((u - u0) / GEOM_STAGES) & 1);
+        const i64 slot = u / tiles, tile = u - slot * tiles;
+        if (slot != cur_slot) { flush(cur_slot); cur_slot = slot; }
+        const bool exists = p.pair0 + slot < p.n_pairs;
+        mbar_wait(full + s, parity);
+        const double2* b = reinterpret_cast<const double2*>(buf + (i64)s * 6 * GEOM_TILE);
+        const i64 f = tile * GEOM_TILE + 2 * threadIdx.x;     // two consecutive frames per thread
+        double c6[6][2];                                       // 16-byte shared loads: a quarter warp reads 128 contiguous bytes
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double2 t = b[k * (GEOM_TILE / 2) + threadIdx.x];
+            c6[k][0] = t.x; c6[k][1] = t.y;
+        }
+        cd g0[2], g1[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double gx = 0.0, gy = 0.0, gz = 0.0, g3 = 0.0;
+            if (exists && f + q < p.N) {
+                double d[3], s2[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) axis_min(c6[2 * ax][q], c6[2 * ax + 1][q], L[ax], d[ax], s2[ax]);
+                const double r2 = __dadd_rn(__dadd_rn(s2[0], s2[1]), s2[2]);
+                double rinv = rsqrt(r2);
+                rinv = rinv * fma(-0.5 * r2, rinv * rinv, 1.5);  // one Newton step: r^-1 to ~1 ulp
+                gx = d[0] * rinv; gy = d[1] * rinv; gz = d[2] * rinv;
+                g3 = rinv * rinv * rinv;
+            }
+            g0[q] = make_double2(gx, gy);
+            g1[q] = make_double2(gz, g3);
+            rs += g3;
+        }
+        if (f < p.N) {   // N is even: frames f and f + 1 exist together
+            cd* out = p.Gs + slot * 2 * p.N;
+            stg256(out + f, g0[0], g0[1]);
+            stg256(out + p.N + f, g1[0], g1[1]);
+        }
+        __syncthreads();                                        // every thread has read stage s: refill it
+        if (threadIdx.x == 0 && u + GEOM_STAGES < u1) issue(u + GEOM_STAGES, s);
+    }
+    flush(cur_slot);
+}
+
 struct ColsTpcParams {
     const cd* Gs;      // [2*items][2][N] geometry streams of the batch (nullptr: all-ones series, "ones" mode)
     i64 items;

@@ -68,5 +68,8 @@ cudaError_t forward_spectrum_real(const SpectrumLoader& ld, const EpiParams& ep,
 cudaError_t forward_spectrum_real2(const SpectrumPairLoader& ld, const EpiParams& ep, i64 n_fft, i64 M, cd* T,
                                    i64 T_cap, const cd* tw, int n_sm, cudaStream_t st);
 cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_spec, i64 M, cudaStream_t st);
+// rows of the packed even-spectra array for `pairs` ragged pairs (7 series each): 14 per two pairs, 8 for a last
+// odd pair (one of them zero); always even
+inline i64 dd_pack_rows(i64 pairs) { return 14 * (pairs / 2) + ((pairs & 1) ? 8 : 0); }
 
 }  // namespace dynpy

@@ -538,34 +538,42 @@ cudaError_t launch_dd_ragged_presence(const int* fidx, const i64* lens, i64 N, i
     return cudaGetLastError();
 }
 
-// G[acc][fidx[pair][k]] += acf[f][k] / (M * N_p^... ) : scatter of per-pair ACFs to frame bins
-// acf holds Re(FFT(P_f))[k] * (1/M) for k < N (n_out = N); f = pair*7 + acc.
+// Packing of the even power spectra of the ragged pairs, two per inverse transform (rows 2t, 2t + 1 of the packed
+// array share transform t).  Two spectra in one transform leak into each other at the level of the rounding error of
+// the LARGER one, and the r^-3-weighted series (columns 3..6, ~ r^-6) are many orders of magnitude below the plain
+// harmonics (columns 0..2, O(1)): like is packed with like.  Per block of two pairs (series o = 0..13, o = 7 pair + c):
+//   (0,1) (2,9) (3,6) (4,5) (7,8) (10,13) (11,12)
+// A last odd pair takes 8 rows; row 3 of its block (series 9 does not exist) is zero.
+__device__ __constant__ signed char c_pos2orig[14] = {0, 1, 2, 9, 3, 6, 4, 5, 7, 8, 10, 13, 11, 12};
+__device__ __constant__ signed char c_orig2pos[14] = {0, 1, 2, 4, 6, 7, 5, 8, 9, 3, 10, 12, 13, 11};
+__device__ __forceinline__ i64 dd_pack_row_of_series(i64 s) { return (s / 14) * 14 + c_orig2pos[s % 14]; }
+__device__ __forceinline__ i64 dd_pack_series_of_row(i64 r) { return (r / 14) * 14 + c_pos2orig[r % 14]; }
+
+// G[acc][fidx[pair][k]] += acf[row][k] / N_p : scatter of per-pair ACFs to frame bins.
+// acf holds Re(FFT(even P))[k] * (1/M) for k < NC, one row per packed row (series = pair*7 + acc).
 __global__ void k_dd_ragged_scatter(const double* __restrict__ acf, const int* __restrict__ fidx,
                                     const i64* __restrict__ lens, i64 N, i64 NC, i64 nfft, double* __restrict__ G) {
-    // series f on gridDim.x (limit 2^31 - 1; gridDim.y stops at 65535 = 9362 pairs), frame chunks on gridDim.y
-    const i64 f = blockIdx.x;
+    // rows on gridDim.x (limit 2^31 - 1; gridDim.y stops at 65535 = 9362 pairs), frame chunks on gridDim.y
+    const i64 row = blockIdx.x;
+    const i64 f = dd_pack_series_of_row(row);
+    if (f >= nfft) return;
     const i64 pl = f / 7;
     const int acc = (int)(f % 7);
     const i64 np = lens[f];
     if (np <= 0) return;
     const double inv = 1.0 / (double)np;
     for (i64 k = (i64)blockIdx.y * blockDim.x + threadIdx.x; k < np; k += (i64)gridDim.y * blockDim.x)
-        atomicAdd(G + (i64)acc * N + fidx[pl * NC + k], acf[f * NC + k] * inv);   // N frames per G row, NC per series
+        atomicAdd(G + (i64)acc * N + fidx[pl * NC + k], acf[row * NC + k] * inv);   // N frames per G row, NC per series
 }
 cudaError_t launch_dd_ragged_scatter(const double* acf, const int* fidx, const i64* lens, i64 N, i64 NC, i64 nfft,
                                      double* G, cudaStream_t st) {
     if (nfft <= 0) return cudaSuccess;
-    const i64 chunk = (i64)7 << 26;   // whole pairs per launch, far below the gridDim.x limit
-    for (i64 f0 = 0; f0 < nfft; f0 += chunk) {
-        i64 cnt = nfft - f0 < chunk ? nfft - f0 : chunk;
-        int gy = (int)((NC + 255) / 256);
-        if (gy > 64) gy = 64;
-        dim3 grid((unsigned)cnt, gy);
-        k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf + f0 * NC, fidx + (f0 / 7) * NC, lens + f0, N, NC, cnt, G);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    const i64 rows = dd_pack_rows(nfft / 7);
+    int gy = (int)((NC + 255) / 256);
+    if (gy > 64) gy = 64;
+    dim3 grid((unsigned)rows, gy);
+    k_dd_ragged_scatter<<<grid, 256, 0, st>>>(acf, fidx, lens, N, NC, nfft, G);
+    return cudaGetLastError();
 }
 
 // Power spectra from the engine's internal order [f][k1][k2] (k = k1 + M1 k2) to natural order [f][k2][k1]:
@@ -605,11 +613,11 @@ cudaError_t launch_spectrum_to_natural(const double* in, double* out, i64 n_spec
 // [0][(4096 - k2) % 4096] for k1 = 0) or already natural (single-pass lengths).  Re FFT(P) = FFT(even part of P):
 // the even parts of two spectra can share one transform (SpectrumPairLoader).
 __global__ void __launch_bounds__(256) k_spectrum_even_natural(const double* __restrict__ in, double* __restrict__ out,
-                                                               int M1) {
+                                                               int M1, i64 f0) {
     __shared__ double tile[32][33];
-    const i64 f = blockIdx.z;
+    const i64 f = f0 + blockIdx.z;
     in += f * (i64)M1 * DYNPY_ROW_LEN;
-    out += f * (i64)M1 * DYNPY_ROW_LEN;
+    out += dd_pack_row_of_series(f) * (i64)M1 * DYNPY_ROW_LEN;
     const int k2_0 = blockIdx.x * 32, k1_0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -631,11 +639,15 @@ __global__ void __launch_bounds__(256) k_spectrum_even_natural(const double* __r
 __global__ void k_spectrum_even_single(const double* __restrict__ in, double* __restrict__ out, i64 M, i64 total) {
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
         const i64 f = e / M, k = e - f * M;
-        out[e] = 0.5 * (in[e] + in[f * M + (k ? M - k : 0)]);
+        out[dd_pack_row_of_series(f) * M + k] = 0.5 * (in[e] + in[f * M + (k ? M - k : 0)]);
     }
 }
 cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_spec, i64 M, cudaStream_t st) {
     if (n_spec <= 0) return cudaSuccess;
+    if ((n_spec / 7) & 1) {   // last odd pair: the partner row of its column 2 does not exist
+        cudaError_t e = cudaMemsetAsync(out + (14 * (n_spec / 14) + 3) * M, 0, (size_t)M * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+    }
     if (M <= DYNPY_ROW_LEN) {
         const i64 total = n_spec * M;
         i64 blocks = (total + 255) / 256;
@@ -647,7 +659,7 @@ cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_sp
     for (i64 f0 = 0; f0 < n_spec; f0 += 32768) {
         const i64 cnt = n_spec - f0 < 32768 ? n_spec - f0 : 32768;
         dim3 grid(DYNPY_ROW_LEN / 32, (unsigned)((M1 + 31) / 32), (unsigned)cnt);
-        k_spectrum_even_natural<<<grid, 256, 0, st>>>(in + f0 * M, out + f0 * M, M1);
+        k_spectrum_even_natural<<<grid, 256, 0, st>>>(in, out, M1, f0);
     }
     return cudaGetLastError();
 }

@@ -60,7 +60,8 @@ class Topology:
                   0..n_isolated-1 and then overwrites them while walking connected_components (which yields
                   single-node components too), so the number the reference ends up with for a molecule of a
                   single frame is n_isolated + mol_rank (`frame_molecule_id`).
-    groups      : list (by mol_rank) of atom-label tuples (ascending).
+    groups      : list (by mol_rank) of atom-label tuples (ascending); built on first use.
+    comp_min[a] : smallest atom of a's component (the canonical name of the component).
     """
 
     def __init__(self, nat: int, bi: np.ndarray, bj: np.ndarray, symbols):
@@ -78,25 +79,77 @@ class Topology:
             deg[b] += 1
             ra, rb = find(a), find(b)
             if ra != rb:
-                parent[max(ra, rb)] = min(ra, rb)
+                parent[max(ra, rb)] = min(ra, rb)   # the root of a component is its smallest atom
         self.nat = nat
         self.symbols = list(symbols)
-        self.mol_rank = np.full(nat, -1, dtype=np.int64)
-        self.n_isolated = int((deg == 0).sum())
-        k = 0
-        seen = {}
-        for a in range(nat):
-            r = find(a)
-            if r not in seen:
-                seen[r] = k
-                k += 1
-            self.mol_rank[a] = seen[r]
-        self.nmol = k
-        self.groups = [[] for _ in range(k)]
-        for a in range(nat):
-            self.groups[self.mol_rank[a]].append(a)
-        self.groups = [tuple(g) for g in self.groups]
+        self.deg = deg
+        self.comp_min = np.array([find(a) for a in range(nat)], dtype=np.int64)
         self.bonds = set(zip(bi.tolist(), bj.tolist()))
+        self._finish()
+
+    def _finish(self):
+        """mol_rank / nmol / n_isolated from comp_min and deg (vectorised: also the whole cost of a derived frame)."""
+        is_min = self.comp_min == np.arange(self.nat)
+        self.mol_rank = (np.cumsum(is_min) - 1)[self.comp_min]
+        self.nmol = int(is_min.sum())
+        self.n_isolated = int((self.deg == 0).sum())
+        self._groups = None
+        self._mol_bonds = None
+
+    @property
+    def groups(self):
+        if self._groups is None:
+            order = np.argsort(self.mol_rank, kind="stable")
+            cuts = np.cumsum(np.bincount(self.mol_rank, minlength=self.nmol))[:-1]
+            self._groups = [tuple(g.tolist()) for g in np.split(order, cuts)]
+        return self._groups
+
+    def bonds_of(self, m: int):
+        """bonds (i, j) inside molecule m"""
+        if self._mol_bonds is None:
+            mb = {}
+            for ij in self.bonds:
+                mb.setdefault(int(self.mol_rank[ij[0]]), []).append(ij)
+            self._mol_bonds = mb
+        return self._mol_bonds.get(int(m), [])
+
+    def derive(self, pairs) -> "Topology":
+        """Topology of a frame whose bond list is this one's with the flags of `pairs` toggled: only the molecules
+        that hold an end of a toggled pair are re-indexed (a handful of atoms), the renumbering of everything behind
+        them is three vectorised passes."""
+        mols = sorted({int(self.mol_rank[a]) for ij in pairs for a in ij})
+        atoms = [a for m in mols for a in self.groups[m]]
+        bonds = set()
+        for m in mols:
+            bonds.update(self.bonds_of(m))
+        toggled = [(int(i), int(j)) for i, j in pairs]
+        bonds.symmetric_difference_update(toggled)
+        parent = {a: a for a in atoms}
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+
+        for a, b in bonds:
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+        t = Topology.__new__(Topology)
+        t.nat, t.symbols = self.nat, self.symbols
+        t.comp_min = self.comp_min.copy()
+        for a in atoms:
+            t.comp_min[a] = find(a)
+        t.deg = self.deg.copy()
+        for ij in toggled:
+            d = -1 if ij in self.bonds else 1
+            t.deg[ij[0]] += d
+            t.deg[ij[1]] += d
+        t.bonds = None          # full bond set of a derived frame: base.bonds ^ toggled (not needed by any caller)
+        t._finish()
+        t._parent, t._touched = self, atoms
+        return t
 
     def frame_molecule_id(self, m):
         """Number compute_molecule gives molecule(s) m when the universe holds this one frame."""
@@ -108,13 +161,15 @@ class Topology:
             out[self.symbols[a]] = out.get(self.symbols[a], 0) + 1
         return out
 
-    def classify_exact(self, identifier: str) -> np.ndarray:
+    def classify_exact(self, identifier) -> np.ndarray:
         """bool per molecule: formula == identifier (Molecule.classify with exact=True).
         Raises KeyError like the reference when nothing matches (universe.py:378)."""
-        want = parse_formula(identifier)
-        syms = sorted({s for s in self.symbols})
-        hit = np.array([all(self.formula(m).get(s, 0) == want.get(s, 0) for s in set(syms) | set(want))
-                        for m in range(self.nmol)], dtype=bool)
+        want = identifier if isinstance(identifier, dict) else parse_formula(identifier)
+        syms = sorted(set(self.symbols) | set(want))
+        code = {s: k for k, s in enumerate(syms)}
+        cnt = np.zeros((self.nmol, len(syms)), dtype=np.int64)
+        np.add.at(cnt, (self.mol_rank, np.array([code[s] for s in self.symbols])), 1)
+        hit = (cnt == np.array([want.get(s, 0) for s in syms])[None, :]).all(axis=1)
         if not hit.any():
             raise KeyError('No records found for {}, with identifier {}.'.format("analyte", want))
         return hit
@@ -133,6 +188,9 @@ class FrameTopologies:
     """The topology of the indexing frame plus the (few) frames whose bond list differs from it — what the
     reference's per-frame compute_molecule sees (universe.py:411-451).
 
+    changes          {frame index: [(i, j), ...]} bond flags that differ from the indexing frame's
+    frames           {frame index: Topology} of the deviating frames — derived from `base` on first use (a run that
+                     never filters by molecule, pair_type 'all', does not pay for them)
     at(f)            Topology of frame index f
     molecule_ids(..) the 'molecule' numbers of the reference's all-frames universe: numbering starts after the
                      isolated atoms of ALL frames, then the components of frame 0, frame 1, ... in atom order
@@ -141,22 +199,28 @@ class FrameTopologies:
     def __init__(self, base: Topology, changes: dict, nframes: int):
         self.base = base
         self.nframes = nframes
-        self.frames = {}
-        for f, pairs in changes.items():
-            bonds = set(base.bonds)
-            for ij in pairs:
-                bonds.symmetric_difference_update([ij])
-            b = sorted(bonds)
-            self.frames[f] = Topology(base.nat, np.array([x[0] for x in b], dtype=np.int64),
-                                      np.array([x[1] for x in b], dtype=np.int64), base.symbols)
-        ncomp = np.full(nframes, base.nmol, dtype=np.int64)
-        niso = np.full(nframes, base.n_isolated, dtype=np.int64)
-        for f, t in self.frames.items():
-            ncomp[f], niso[f] = t.nmol, t.n_isolated
-        self._start = int(niso.sum()) + np.concatenate([[0], np.cumsum(ncomp)[:-1]])
+        self.changes = changes
+        self._frames = None
+        self._start_ = None
+
+    @property
+    def frames(self) -> dict:
+        if self._frames is None:
+            self._frames = {f: self.base.derive(pairs) for f, pairs in self.changes.items()}
+        return self._frames
+
+    @property
+    def _start(self):
+        if self._start_ is None:
+            ncomp = np.full(self.nframes, self.base.nmol, dtype=np.int64)
+            niso = np.full(self.nframes, self.base.n_isolated, dtype=np.int64)
+            for f, t in self.frames.items():
+                ncomp[f], niso[f] = t.nmol, t.n_isolated
+            self._start_ = int(niso.sum()) + np.concatenate([[0], np.cumsum(ncomp)[:-1]])
+        return self._start_
 
     def at(self, f: int) -> Topology:
-        return self.frames.get(f, self.base)
+        return self.frames[f] if f in self.changes else self.base
 
     def molecule_ids(self, first_atoms) -> np.ndarray:
         """[F, len(first_atoms)]: id, in every frame, of the molecule that holds each of the given atoms."""
@@ -187,7 +251,7 @@ def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra
             ev = ops.topology_events(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
             changes = {}
             for f, i, j in ev.tolist():
-                changes.setdefault(int(f), []).append((int(i), int(j)))
+                changes.setdefault(f, []).append((i, j))
             return FrameTopologies(topo, changes, F), two0
         bad, first = ops.topology_check(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
         if bad:

@@ -364,3 +364,34 @@ def test_qr_missing_values_follow_reference_complex_arithmetic():
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-15)
     clean = np.arange(12.0).reshape(6, 2)
     assert qrax._fill_missing(clean) is clean
+
+
+def test_derived_topology_equals_full_reindexing():
+    """Topology.derive (only the molecules that hold an end of a toggled bond are re-indexed) against a full
+    union-find of the toggled bond list: random graphs with isolated atoms, bonds added (merges) and removed
+    (splits, new isolated atoms)."""
+    from dynpy_b200 import topology
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        A = int(rng.integers(8, 60))
+        nb = int(rng.integers(0, A))
+        iu, ju = np.triu_indices(A, k=1)
+        pick = rng.choice(len(iu), size=min(nb, len(iu)), replace=False)
+        bonds = sorted(zip(iu[pick].tolist(), ju[pick].tolist()))
+        sym = ["H" if a % 3 else "O" for a in range(A)]
+        base = topology.Topology(A, np.array([b[0] for b in bonds], dtype=np.int64),
+                                 np.array([b[1] for b in bonds], dtype=np.int64), sym)
+        ntog = int(rng.integers(1, 5))
+        cand = [bonds[k] for k in rng.choice(len(bonds), size=min(ntog, len(bonds)), replace=False)] if bonds else []
+        extra = rng.choice(len(iu), size=ntog, replace=False)
+        toggled = sorted(set(cand[:ntog // 2 + 1]) | {(int(iu[k]), int(ju[k])) for k in extra[:ntog // 2 + 1]})
+        new = sorted(set(bonds) ^ set(toggled))
+        full = topology.Topology(A, np.array([b[0] for b in new], dtype=np.int64),
+                                 np.array([b[1] for b in new], dtype=np.int64), sym)
+        der = base.derive(toggled)
+        np.testing.assert_array_equal(der.mol_rank, full.mol_rank)
+        assert (der.nmol, der.n_isolated) == (full.nmol, full.n_isolated)
+        assert der.groups == full.groups
+        np.testing.assert_array_equal(der.classify_exact({"O": 1, "H": 2}) if any(
+            full.formula(m) == {"O": 1, "H": 2} for m in range(full.nmol)) else [], full.classify_exact(
+            {"O": 1, "H": 2}) if any(full.formula(m) == {"O": 1, "H": 2} for m in range(full.nmol)) else [])

@@ -20,11 +20,23 @@ def t(fn, reps=3):
     return (time.time() - t0) / reps, out
 dt_wrap, w = t(lambda: ops.wrap(raw, L))
 dt_topo, (ft, two0) = t(lambda: topology.build_topology(w, box.symbols, cell, L, bond_extra=0.45, dynamic=True))
+# breakdown: the device scan alone, then the host re-indexing of the deviating frames
+from dynpy_b200.elements import SYM2COVRAD as _RC
+_two0 = topology.frame_pairs(w, cell, 0, L)
+_b0 = topology.bonded(_two0, box.symbols, 0.45)
+_exp = torch.zeros((raw.shape[0], raw.shape[0]), dtype=torch.uint8)
+_exp[torch.from_numpy(_two0["i"][_b0]), torch.from_numpy(_two0["j"][_b0])] = 1
+_exp = _exp.cuda()
+_rc = torch.tensor([_RC[s] for s in box.symbols], dtype=torch.float64, device="cuda")
+dt_scan, ev = t(lambda: ops.topology_events(w, _rc, 0.45, _exp, cell, L))
+dt_fp, _ = t(lambda: topology.frame_pairs(w, cell, 0, L))
+print("  device scan (topology_events) %.2f ms = %.3e atom-pair-frames/s, %d events; frame-0 pair table %.2f ms"
+      % (dt_scan * 1e3, raw.shape[0] * (raw.shape[0] - 1) / 2 * F / dt_scan, len(ev), dt_fp * 1e3))
 dt_sel, (pi, pj, ch) = t(lambda: DDparse.select_pairs_dynamic(box.symbols, ft, 3, "all", None))
 A = raw.shape[0]
 print("atoms %d frames %d: wrap %.2f ms, build_topology %.2f ms (%.3e atom-pair-frames/s), select_pairs %.2f ms, "
       "deviating frames %d, pairs %d" % (A, F, dt_wrap * 1e3, dt_topo * 1e3, A * (A - 1) / 2 * F / dt_topo, dt_sel * 1e3,
-                                         len(ft.frames), len(pi)))
+                                         len(ft.changes), len(pi)))
 
 # cross-check of the device scan against a brute-force torch evaluation on the first frames
 from dynpy_b200.elements import SYM2COVRAD
