@@ -560,9 +560,14 @@ static i64 dd_ragged_pair_bytes(i64 N, i64 M) {
 // one spare row of the packed even spectra and of the ACFs (odd pair counts: see dd_pack_rows)
 static i64 dd_ragged_extra_bytes(i64 N, i64 M) { return align_up(M * 8, 256) + align_up(N * 8, 256); }
 
+// Transforms the four-step intermediate T of the ragged path holds: 14 for small calls (46 MB at M = 204800: stays in
+// L2), 224 from 32 pairs on — with 14 a launch covers 700 rows of 4096 points on 296 CTAs and the path was bound by
+// launch tails (66 000 launches of ~20 us per cfg2 step at rmax = 15 bohr).
+static i64 dd_ragged_tcap(i64 pairs) { return pairs >= 32 ? 224 : 14; }
+
 int64_t dynpy_dd_ragged_workspace_bytes(int64_t n_frames, int64_t M, int64_t pairs) {
     if (pairs < 1) pairs = 1;
-    i64 t = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;  // T for >= 14 transforms in flight
+    i64 t = M > DYNPY_ROW_LEN ? dd_ragged_tcap(pairs) * M * (i64)sizeof(cd) : 0;
     return pairs * dd_ragged_pair_bytes(n_frames, M) + t + 4096 + dd_ragged_extra_bytes(n_frames, M);
 }
 
@@ -604,8 +609,14 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
     rc = get_device_state(&d, st);
     if (rc) return rc;
     const i64 N = n_frames, NC = n_cap;
-    const i64 tbytes = M > DYNPY_ROW_LEN ? 14 * M * (i64)sizeof(cd) : 0;
+    i64 T_cap = M > DYNPY_ROW_LEN ? dd_ragged_tcap(n_pairs) : 0;
+    i64 tbytes = T_cap * M * (i64)sizeof(cd);
     i64 cap = (ws_bytes - tbytes - 4096 - dd_ragged_extra_bytes(NC, M)) / dd_ragged_pair_bytes(NC, M);
+    if (cap < 32 && T_cap > 14) {   // a workspace sized for a small batch: the small T
+        T_cap = 14;
+        tbytes = T_cap * M * (i64)sizeof(cd);
+        cap = (ws_bytes - tbytes - 4096 - dd_ragged_extra_bytes(NC, M)) / dd_ragged_pair_bytes(NC, M);
+    }
     if (cap < 1) {
         set_error("dynpy_dd_pairs_ragged_to_acf_f64: workspace too small (need >= %lld bytes)",
                   (long long)dynpy_dd_ragged_workspace_bytes(NC, M, 1));
@@ -624,7 +635,6 @@ int dynpy_dd_pairs_ragged_capped_f64(const double* coords, int64_t n_atoms, int6
     double* Pn = (double*)carve((cap * 7 + 1) * M * 8);
     double* acf = (double*)carve((cap * 7 + 1) * NC * 8);
     cd* T = tbytes ? (cd*)carve(tbytes) : nullptr;
-    const i64 T_cap = tbytes ? 14 : 0;
 
     for (i64 p0 = 0; p0 < n_pairs; p0 += cap) {
         const i64 cnt = n_pairs - p0 < cap ? n_pairs - p0 : cap;

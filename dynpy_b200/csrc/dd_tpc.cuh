@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(GEOM_NT, 2) k_dd_geom_tma(const GeomParams p) 
 }
 
 struct ColsTpcParams {
-    const cd* Gs;      // [2*items][2][N] geometry streams of the batch (nullptr: all-ones series, "ones" mode)
+    const cd* Gs;      // [2*items][2][N] geometry streams of the batch
     i64 items;
     i64 pair0, n_pairs; // first pair of the batch / total pairs (pair q of the last item may not exist)
     i64 N;
-    cd* T;             // [items][11][M1][DYNPY_T_RS]   (ones mode: [M1][DYNPY_T_RS])
+    cd* T;             // [items][11][M1][DYNPY_T_RS]
     i64 M;
     const cd* seeds;   // [4096][2]: W_M^{n2}, W_M^{2 n2}
     int sync_units;    // 1: CTA barrier once per series
@@ -390,6 +390,43 @@ __device__ __forceinline__ void cp_async16_zfill(cd* smem_dst, const cd* gsrc, b
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
 
+// Immediate-offset forms: the H copies of a stream (and the M1 stores of a series) differ from one base address by
+// compile-time constants, which fit the 24-bit offset field of LDGSTS / STG.  With the addresses passed as computed
+// pointers the compiler materialised every 64-bit address (and every source size) before the first copy: 75
+// registers per burst, spilled.
+template <int SOFF, int GOFF>
+__device__ __forceinline__ void cp_async16_zfill_at(unsigned sa, const cd* gsrc, bool off) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cp.async.cg.shared.global [%0 + %3], [%1 + %4], 16, p;\n"   // p: ignore-src, the 16 bytes are zero-filled
+        "}\n" ::"r"(sa), "l"(gsrc), "r"((int)off), "n"(SOFF), "n"(GOFF) : "memory");
+}
+template <int STRIDE_S, int STRIDE_G, int... J>
+__device__ __forceinline__ void cp_async_burst(unsigned sa, const cd* gsrc, int jlim, std::integer_sequence<int, J...>) {
+    (cp_async16_zfill_at<J * STRIDE_S, J * STRIDE_G>(sa, gsrc, J >= jlim), ...);
+}
+template <i64 GOFF>
+__device__ __forceinline__ void st_stream_at(cd* p, cd v) {
+    asm volatile("st.global.cs.v2.f64 [%0 + %3], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y), "n"(GOFF) : "memory");
+}
+
+// outputs k1 = 2 a + PAR of a column, a = A..H-1, times the running inter-pass twiddle (w advances by w2 per output;
+// the first even output carries no twiddle)
+template <int H, int PAR, int A>
+__device__ __forceinline__ void tpc_store_chain(cd* dst, const cd (&v)[H], cd w, const cd w2, bool live) {
+    if constexpr (A < H) {
+        constexpr bool plain = PAR == 0 && A == 0;
+        const cd val = plain ? v[A] : cmul(v[A], w);
+        if (live) st_stream_at<(i64)(2 * A + PAR) * DYNPY_T_RS * (i64)sizeof(cd)>(dst, val);
+        if (!plain && A + 1 < H) w = cmul(w, w2);
+        tpc_store_chain<H, PAR, A + 1>(dst, v, w, w2, live);
+    }
+}
+
+template <int K> struct TpcKind { static constexpr int value = K; };
+
 template <int M1>
 __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols_tpc(const ColsTpcParams p) {
     constexpr int H = M1 / 2;
@@ -401,18 +438,17 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
     // cp.async burst each: all H loads of a stream are in flight together, L2 latency is paid twice per
     // series instead of once per frame), then the stash of the H samples for the odd half
     cd* zone = smem + threadIdx.x;
-    const bool ones = p.Gs == nullptr;
-    const int nslots = ones ? 1 : 11;
-    const i64 units = (ones ? 1 : p.items) * NCB * nslots;
+    constexpr int nslots = 11;
+    const i64 units = p.items * NCB * nslots;
     const int nfr = (int)(p.N < (i64)H * 4096 ? p.N : (i64)H * 4096);  // frames beyond M/2 do not exist
-    const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
-    const double KF = 1.5853309190424043;
+    constexpr double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
+    constexpr double KF = 1.5853309190424043;
     constexpr i64 TS = (i64)M1 * DYNPY_T_RS;
     const i64 N = p.N;
 
     // stream A of a unit: (x/r, y/r) of the series' pair, or (z/r, r^-3) of pair p for the packed series
     auto issue_stream = [&](i64 u, int which) {
-        if (u < units && !ones) {
+        if (u < units) {
             const int slot = (int)(u % nslots);
             const i64 ic = u / nslots;
             const int n2 = (int)(ic % NCB) * TPC_THREADS + threadIdx.x;
@@ -425,8 +461,8 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
             const int jlim = (nfr > n2 && (!RAGGED || n2 < 4096)) ? (nfr - n2 + 4095) >> 12 : 0;
             // rows j >= jlim are zero-filled (src-size 0: nothing is read; the address still lies inside the
             // workspace, whose T region follows the geometry streams)
-#pragma unroll
-            for (int j = 0; j < H; ++j) cp_async16_zfill(zone + j * TPC_THREADS, src + (j << 12), j < jlim);
+            cp_async_burst<TPC_THREADS * 16, 4096 * 16>((unsigned)__cvta_generic_to_shared(zone), src, jlim,
+                                                         std::make_integer_sequence<int, H>{});
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -441,84 +477,81 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         const cd w1 = ldg_cd(p.seeds + 2 * (n2 & 4095)), w2 = ldg_cd(p.seeds + 2 * (n2 & 4095) + 1);
         cd* dst = p.T + (item * nslots + slot) * TS + n2;
         // slot -> series (kernels.h): 0 Y20 p+iq | 1,2 Y21 p,q | 3,4 Y22 p,q | 5 r^-3 p+iq | 6 F20 p+iq | 7,8 F21 p,q | 9,10 F22 p,q
-        const bool packed = slot == 0 || slot == 5 || slot == 6;
-        const bool weighted = slot >= 6;                       // carries r^-3 (F2m)
-        const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;  // (x + i y)^1 z, else (x + i y)^2
-        const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
         const int jlim = (nfr > n2 && live) ? (nfr - n2 + 4095) >> 12 : 0;
         if (p.sync_units) __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)
         cd v[H];
-        if (ones) {
-#pragma unroll
-            for (int j = 0; j < H; ++j) v[j] = make_double2(j < jlim ? 1.0 : 0.0, 0.0);
-        } else {
-            // ---- stream A
+        // Series formation, one specialised straight-line block per kind of series (the slot is uniform over the
+        // CTA: a branch, no selects).  Frames beyond the series (j >= jlim) and the missing second pair of a last
+        // odd item arrive as zero geometry (zero-filled copies / zero-filled streams), which makes every series
+        // that carries a factor x, y, z or r^-3 vanish by itself; only Y20 = C20 (3 z^2 - 1) and r^-3 - <r^-3>
+        // need their constant term switched off there.
+        auto form = [&](auto kind) {
+            constexpr int K = decltype(kind)::value;   // 0 Y20 | 5 r^-3 | 6 F20 | 1 Y21 | 3 Y22 | 7 F21 | 9 F22
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (packed) {
-                // slot 5 is r^-3 - <r^-3> (ddrax.py:292): the per-pair sums are complete (k_dd_geom ran before)
-                const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
-                const double mean = slot == 5 ? __ldg(p.rsum + 2 * item) * p.inv_n : 0.0;
+            if constexpr (K == 0 || K == 5 || K == 6) {
+                const bool q_exists = p.pair0 + 2 * item + 1 < p.n_pairs;
+                const int jlim_q = q_exists ? jlim : 0;
+                const double mean_p = K == 5 ? __ldg(p.rsum + 2 * item) * p.inv_n : 0.0;
+                const double mean_q = K == 5 ? __ldg(p.rsum + 2 * item + 1) * p.inv_n : 0.0;   // 0 for a missing pair
+                auto real_word = [&](const cd zr, int j, int lim, double mean) -> double {
+                    if constexpr (K == 0) return (j < lim ? C20 : 0.0) * fma(3.0 * zr.x, zr.x, -1.0);
+                    else if constexpr (K == 5) return zr.y - (j < lim ? mean : 0.0);
+                    else return (KF * C20) * zr.y * fma(3.0 * zr.x, zr.x, -1.0);
+                };
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * TPC_THREADS];
-                    const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
-                    v[j].x = j < jlim ? (slot == 0 ? c : c * zr.y) * y - mean : 0.0;
-                }
+                for (int j = 0; j < H; ++j) v[j].x = real_word(zone[j * TPC_THREADS], j, jlim, mean_p);
+                issue_stream(u, 1);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < H; ++j) v[j].y = real_word(zone[j * TPC_THREADS], j, jlim_q, mean_q);
             } else {
+                constexpr bool order1 = K == 1 || K == 7;
+                constexpr bool weighted = K >= 7;
+                constexpr double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
+                if constexpr (K == 3) {
+                    // Y22 = C22 (x + i y)^2 needs neither z nor r^-3: no second stream (and none of its latency)
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const cd xy = zone[j * TPC_THREADS];
-                    v[j] = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                    for (int j = 0; j < H; ++j) {
+                        const cd xy = zone[j * TPC_THREADS];
+                        v[j] = make_double2(c * (xy.x * xy.x - xy.y * xy.y), (2.0 * c) * xy.x * xy.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) {
+                        const cd xy = zone[j * TPC_THREADS];
+                        v[j] = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                    }
+                    issue_stream(u, 1);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < H; ++j) {
+                        const cd zr = zone[j * TPC_THREADS];
+                        const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
+                        v[j] = make_double2(sc * v[j].x, sc * v[j].y);
+                    }
                 }
             }
-            // ---- stream B into the same zone
-            issue_stream(u, 1);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (packed) {
-                const double c = slot == 5 ? 1.0 : (weighted ? KF * C20 : C20);
-                const double mean = slot == 5 ? __ldg(p.rsum + 2 * item + 1) * p.inv_n : 0.0;
-#pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * TPC_THREADS];
-                    const double y = slot == 5 ? 1.0 : fma(3.0 * zr.x, zr.x, -1.0);
-                    v[j].y = (j < jlim && q_exists) ? (slot == 0 ? c : c * zr.y) * y - mean : 0.0;
-                }
-            } else {
-                const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
-#pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const cd zr = zone[j * TPC_THREADS];
-                    const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
-                    v[j] = make_double2(sc * v[j].x, sc * v[j].y);
-                }
-            }
+        };
+        switch (slot) {
+            case 0: form(TpcKind<0>{}); break;
+            case 5: form(TpcKind<5>{}); break;
+            case 6: form(TpcKind<6>{}); break;
+            case 1: case 2: form(TpcKind<1>{}); break;
+            case 3: case 4: form(TpcKind<3>{}); break;
+            case 7: case 8: form(TpcKind<7>{}); break;
+            default: form(TpcKind<9>{}); break;
         }
 #pragma unroll
         for (int j = 0; j < H; ++j) zone[j * TPC_THREADS] = v[j];
         // even outputs
         ColCodelets<H>::even(v);
-        {
-            cd w = w2;
-            if (live) st_stream(dst, v[0]);
-#pragma unroll
-            for (int a = 1; a < H; ++a) {
-                if (live) st_stream(dst + (i64)(2 * a) * DYNPY_T_RS, cmul(v[a], w));
-                if (a + 1 < H) w = cmul(w, w2);
-            }
-        }
+        tpc_store_chain<H, 0, 0>(dst, v, w2, w2, live);
         // odd outputs
 #pragma unroll
         for (int j = 0; j < H; ++j) v[j] = zone[j * TPC_THREADS];
         issue_stream(u + gridDim.x, 0);  // the zone is free: next series' first stream lands under the odd half
         ColCodelets<H>::odd(v);
-        {
-            cd w = w1;
-#pragma unroll
-            for (int a = 0; a < H; ++a) {
-                if (live) st_stream(dst + (i64)(2 * a + 1) * DYNPY_T_RS, cmul(v[a], w));
-                if (a + 1 < H) w = cmul(w, w2);
-            }
-        }
+        tpc_store_chain<H, 1, 0>(dst, v, w1, w2, live);
     }
 }
 

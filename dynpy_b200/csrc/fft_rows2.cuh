@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     if (u0 >= u1) return;
 
     const int h = tid >> 4, m = tid & 15;
+    // padded shared-memory indices (pad16(i) = i + i / 16) written out as base + constant: pad16(tid + 256 k) =
+    // pad16(tid) + 272 k, pad16(256 h + 16 q + m) = 272 h + m + 17 q, pad16(16 tid + q) = 17 tid + q
+    const int b1 = tid + h, b2 = 272 * h + m, b3 = 17 * tid;
     // step-2 merged twiddle chain: c0 = W_4096^{m h}, step = W_256^m
     const cd c0 = ldg_cd(p.twp + m * h);
     const cd cs = ldg_cd(p.twp + 16 * m);
@@ -77,13 +80,26 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.0;
 
-    auto row_ptr = [&](i64 u, int& slot, int& k1, i64& item) -> const cd* {
+    // position in the unit list (slot index, k1, item; item fastest): decoded once by division, then advanced by
+    // increments (the two 64-bit divisions per row cost ~240 instructions between steps 1 and 2)
+    struct Cursor { int si, k1; i64 item; };
+    auto decode = [&](i64 u) -> Cursor {
+        Cursor c;
         const i64 sk = u / p.items;
-        item = u - sk * p.items;
-        const int si = (int)(sk / p.M1);
-        k1 = (int)(sk - (i64)si * p.M1);
-        slot = (int)((p.sel_pack >> (4 * si)) & 15ull);
-        return p.T + ((item * p.nslots + slot) * p.M1 + k1) * (i64)p.rs;
+        c.item = u - sk * p.items;
+        c.si = (int)(sk / p.M1);
+        c.k1 = (int)(sk - (i64)c.si * p.M1);
+        return c;
+    };
+    auto advance = [&](Cursor& c) {
+        if (++c.item == p.items) {
+            c.item = 0;
+            if (++c.k1 == p.M1) { c.k1 = 0; ++c.si; }
+        }
+    };
+    auto slot_of = [&](const Cursor& c) -> int { return (int)((p.sel_pack >> (4 * c.si)) & 15ull); };
+    auto ptr_of = [&](const Cursor& c) -> const cd* {
+        return p.T + ((c.item * p.nslots + slot_of(c)) * p.M1 + c.k1) * (i64)p.rs;
     };
     auto flush = [&](int slot, int k1) {
         double* sr = reinterpret_cast<double*>(smem);
@@ -100,9 +116,11 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
 
     // element n2 = tid + 256 q of a row: tile (tid / TILE) + (256 / TILE) q, offset tid % TILE
     auto t_off = [&](int q) -> i64 { return tid + 256 * q; };
-    int slot, k1;
-    i64 item;
-    const cd* src = row_ptr(u0, slot, k1, item);
+    Cursor cur = decode(u0);
+    Cursor pfc = decode(u0 + (p.pf_dist > 0 ? p.pf_dist : 0) < u1 ? u0 + (p.pf_dist > 0 ? p.pf_dist : 0) : u0);   // prefetch cursor
+    int slot = slot_of(cur), k1 = cur.k1;
+    i64 item = cur.item;
+    const cd* src = ptr_of(cur);
 
     cd nx[16];
 #pragma unroll
@@ -124,31 +142,36 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         }
         // ---- step 1
         fft16(v);
-        smem[pad16(tid)] = v[0];
+        smem[b1] = v[0];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) smem[pad16(k * 256 + tid)] = cmul(v[k], stw1[k * 16 + h]);
+        for (int k = 1; k < 16; ++k) smem[b1 + 272 * k] = cmul(v[k], stw1[k * 16 + h]);
         __syncthreads();
         // next row: decode now (its registers are loaded under step 3); the row after it is pulled into
         // L2 by one bulk prefetch per chunk (DRAM latency under this load is several microseconds)
         int nslot = slot, nk1 = k1;
         i64 nitem = item;
-        if (u + 1 < u1) src = row_ptr(u + 1, nslot, nk1, nitem);
-        if (p.pf_dist > 0 && u + p.pf_dist < u1 && tid == 0) {
-            int s2, k2;
-            i64 i2;
-            const cd* pf = row_ptr(u + p.pf_dist, s2, k2, i2);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(4096 * 16) : "memory");
+        if (u + 1 < u1) {
+            advance(cur);
+            src = ptr_of(cur);
+            nslot = slot_of(cur); nk1 = cur.k1; nitem = cur.item;
+        }
+        if (p.pf_dist > 0 && u + p.pf_dist < u1) {
+            if (tid == 0) {
+                const cd* pf = ptr_of(pfc);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(4096 * 16) : "memory");
+            }
+            advance(pfc);
         }
         // ---- step 2
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = smem[pad16(h * 256 + q * 16 + m)];
+        for (int q = 0; q < 16; ++q) v[q] = smem[b2 + 17 * q];
         fft16(v);
         {
             cd w = c0;
             asm volatile("" : "+d"(w.x), "+d"(w.y));  // keep the chain inside the loop (15 hoisted values would spill)
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                smem[pad16(h * 256 + k * 16 + m)] = cmul(v[k], w);
+                smem[b2 + 17 * k] = cmul(v[k], w);
                 if (k < 15) w = cmul(w, cs);
             }
         }
@@ -158,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         __syncwarp();
         // ---- step 3
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = smem[pad16(tid * 16 + q)];
+        for (int q = 0; q < 16; ++q) v[q] = smem[b3 + q];
 #pragma unroll
         for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
         __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten

@@ -181,8 +181,12 @@ static int parse_blocks(const char* path, int64_t nat, int32_t header_lines, int
         return nullptr;
     };
 
-    // ---- pass 2: parse the selected frames
-    std::atomic<int64_t> nextf{0};
+    // ---- pass 2: parse the selected frames.  The frames are cut into contiguous pieces; a piece locates its first
+    // block through the newline index once and then walks forward (frames not selected in between are skipped line
+    // by line), so the text is scanned once — locating every frame through the index re-scanned half a chunk
+    // (tens of MB) per frame.
+    const int64_t npieces = n_printed < (int64_t)nt * 8 ? n_printed : (int64_t)nt * 8;
+    std::atomic<int64_t> nextp{0};
     std::atomic<int> bad{0};
     std::string errmsg;
     std::atomic<bool> err_set{false};
@@ -191,9 +195,22 @@ static int parse_blocks(const char* path, int64_t nat, int32_t header_lines, int
         bool exp = false;
         if (err_set.compare_exchange_strong(exp, true)) errmsg = msg;
     };
+    auto skip_lines = [&](const char* s, int64_t n) -> const char* {
+        while (n > 0 && s < end) {
+            const char* q = (const char*)memchr(s, '\n', (size_t)(end - s));
+            if (!q) return n == 1 ? end : nullptr;
+            s = q + 1;
+            --n;
+        }
+        return n == 0 ? s : nullptr;
+    };
     auto parse = [&]() {
-        for (int64_t k; (k = nextf.fetch_add(1)) < n_printed && !bad.load();) {
-            const char* s = line_start((printed_host[k] - 1) * blk);
+      for (int64_t piece; (piece = nextp.fetch_add(1)) < npieces && !bad.load();) {
+        const int64_t k0 = n_printed * piece / npieces, k1 = n_printed * (piece + 1) / npieces;
+        const char* s = nullptr;
+        for (int64_t k = k0; k < k1 && !bad.load(); ++k) {
+            s = (k == k0) ? line_start((printed_host[k] - 1) * blk)
+                          : skip_lines(s, (printed_host[k] - printed_host[k - 1] - 1) * blk);
             if (!s) { fail("internal: line index out of range"); return; }
             if (header_first_host) {
                 const char* le = (const char*)memchr(s, '\n', (size_t)(end - s));
@@ -239,6 +256,7 @@ static int parse_blocks(const char* path, int64_t nat, int32_t header_lines, int
                 s = le < end ? le + 1 : end;
             }
         }
+      }
     };
     {
         std::vector<std::thread> th;

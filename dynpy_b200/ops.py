@@ -361,6 +361,9 @@ def dd_pairs_ragged_to_acf(coords, pair_i, pair_j, cell, rmax, M=None, G=None, w
         nb = max(1, min(n, (ws_budget - (one - per)) // per))
         with torch.cuda.device(coords.device):
             wsb = int(lib.dynpy_dd_ragged_workspace_bytes(n_cap, Mc, nb))
+            while wsb > ws_budget and nb > 1:      # larger calls carry a larger T (not linear in the pair count)
+                nb = max(1, nb - max(1, -(-(wsb - ws_budget) // per)))
+                wsb = int(lib.dynpy_dd_ragged_workspace_bytes(n_cap, Mc, nb))
             ws = workspace(coords.device, wsb)
             rc = lib.dynpy_dd_pairs_ragged_capped_f64(coords.data_ptr(), A, F, pi.data_ptr(), pj.data_ptr(), n,
                                                       float(cell[0]), float(cell[1]), float(cell[2]), float(rmax),
