@@ -5,6 +5,7 @@
 #include "fft_rows2.cuh"
 #include "kernels.h"
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace dynpy {
@@ -14,7 +15,7 @@ static inline i64 align_up2(i64 x, i64 a) { return (x + a - 1) / a * a; }
 bool dd2_supported(i64 M) {
     const i64 m1 = M >> 12;
     return (M & 4095) == 0 && (m1 == 16 || m1 == 20 || m1 == 24 || m1 == 32 || m1 == 40 || m1 == 50 || m1 == 64 ||
-                               m1 == 512);
+                               m1 == 128 || m1 == 256 || m1 == 512);
 }
 
 // bytes of one padded transform of T
@@ -27,14 +28,49 @@ i64 dd2_workspace_bytes(i64 M, i64 N, i64 items) {
            items * DD_NSLOTS * t_bytes(M) + 1024;
 }
 
-// long columns (M1 = 512): two-level thread-per-column kernel, C columns per CTA
+// long columns (M1 = 128, 256, 512): two-level thread-per-column kernel, C columns per CTA
 #ifndef TPC2_C
 #define TPC2_C 4
 #endif
+template <int B, int C, int PER, bool GS>
+static cudaError_t launch_cols_tpc3_shape(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
+    const size_t smem3 = Tpc3Shape<B, C>::smem_bytes(GS);
+    auto kern = k_cols_tpc3<B, C, PER, GS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e != cudaSuccess) return e;
+    const int tiles = 4096 / C;
+    int gy = (4 * PER * n_sm + tiles - 1) / tiles;   // >= 4 waves
+    if (gy > p.items) gy = (int)p.items;
+    if (gy < 1) gy = 1;
+    kern<<<dim3(tiles, gy), Tpc3Shape<B, C>::NT, smem3, st>>>(p, tw);
+    return cudaGetLastError();
+}
+template <int B, int C>
+static cudaError_t launch_cols_tpc3_B(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st, int per, int gs) {
+    // per = CTAs per SM = register budget (2: 255, 3: 168, 4: 128); gs: geometry staged in shared memory
+    if (gs) return per == 2 ? launch_cols_tpc3_shape<B, C, 2, true>(p, tw, n_sm, st)
+                 : per == 4 ? launch_cols_tpc3_shape<B, C, 4, true>(p, tw, n_sm, st)
+                            : launch_cols_tpc3_shape<B, C, 3, true>(p, tw, n_sm, st);
+    return per == 3 ? launch_cols_tpc3_shape<B, C, 3, false>(p, tw, n_sm, st)
+         : per == 4 ? launch_cols_tpc3_shape<B, C, 4, false>(p, tw, n_sm, st)
+                    : launch_cols_tpc3_shape<B, C, 2, false>(p, tw, n_sm, st);
+}
 static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);
+    const int m1 = (int)(p.M >> 12);
+    const char* pe = getenv("DYNPY_TPC3_PER_SM");   // A/B knobs: CTAs per SM, geometry staging (DYNPY_TPC3_GS=0|1)
+    const char* ge = getenv("DYNPY_TPC3_GS");
+    // measured (96 pairs, tools/dbg/probe_dd.py): 512-point columns 6.08 ms with the geometry in registers at 2 CTAs
+    // per SM, 5.60 staged in shared memory at 3; 256-point: 2.39 / 2.28; 128-point: registers at 3 CTAs (1.13 vs 1.23)
+    const int gs = ge ? atoi(ge) : (m1 == 128 ? 0 : 1);
+    const int per = pe ? atoi(pe) : 3;
+    if (m1 == 256) return launch_cols_tpc3_B<16, 8>(p, tw, n_sm, st, per, gs);   // 128 threads, fft16 per phase-C thread
+    if (m1 == 128) return launch_cols_tpc3_B<8, 8>(p, tw, n_sm, st, per, gs);    // 128 threads, fft8 per phase-C thread
     constexpr int B = 32, C = TPC2_C;
     const size_t smem = (size_t)16 * B * C * sizeof(cd);
+    const char* en = getenv("DYNPY_TPC2");
+    const int v3 = (en && en[0] == 'o') ? 0 : 1;   // "old": per-series loads (A/B)
+    if (v3) return launch_cols_tpc3_B<B, C>(p, tw, n_sm, st, per, gs);
     cudaError_t e = cudaFuncSetAttribute(k_cols_tpc2<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int tiles = 4096 / C;
@@ -42,22 +78,7 @@ static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_
     int gy = (4 * per_sm * n_sm + tiles - 1) / tiles;   // >= 4 waves
     if (gy > p.items) gy = (int)p.items;
     if (gy < 1) gy = 1;
-    const char* en = getenv("DYNPY_TPC2");
-    const int v3 = (en && en[0] == 'o') ? 0 : 1;   // "old": per-series loads (A/B)
-    if (v3) {
-        const char* pe = getenv("DYNPY_TPC3_PER_SM");
-        const int per = pe ? atoi(pe) : 2;   // 2 x 128 threads at 254 registers (no spills) measured faster than 3 x 128 at 168
-        const size_t smem3 = smem + (size_t)16 * B * sizeof(cd);
-        auto kern = per == 2 ? k_cols_tpc3<B, C, 2> : k_cols_tpc3<B, C, 3>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-        if (e != cudaSuccess) return e;
-        gy = (4 * per * n_sm + tiles - 1) / tiles;
-        if (gy > p.items) gy = (int)p.items;
-        if (gy < 1) gy = 1;
-        kern<<<dim3(tiles, gy), B * C, smem3, st>>>(p, tw);
-    } else {
-        k_cols_tpc2<B, C><<<dim3(tiles, gy), B * C, smem, st>>>(p, tw);
-    }
+    k_cols_tpc2<B, C><<<dim3(tiles, gy), B * C, smem, st>>>(p, tw);
     return cudaGetLastError();
 }
 
@@ -90,7 +111,7 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
     if (units <= 0) return cudaSuccess;
     {
         static int pf = -1;
-        if (pf < 0) { const char* e = getenv("DYNPY_ROWS_PF"); pf = e ? atoi(e) : 2; }
+        if (pf < 0) { const char* e = getenv("DYNPY_ROWS_PF"); pf = e ? atoi(e) : 1; }
         p.pf_dist = pf;
     }
     int grid = 2 * n_sm;
@@ -120,7 +141,10 @@ static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStre
     k_cols_tpc<M1><<<per_sm * n_sm, TPC_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
-static cudaError_t launch_cols_tpc(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
+// noinline: inlined into dd2_run, gcc 13 (-O3) unswitched the batch loop on the alignment test of the geometry branch
+// and dropped the cases 16..64 of this switch from the unaligned copy — every N % 4 != 0 call then returned
+// cudaErrorInvalidValue from the default branch (found by test_dd_geometry_kernel_variants_agree[99998])
+static __attribute__((noinline)) cudaError_t launch_cols_tpc(const ColsTpcParams& p, const cd* tw, int n_sm, cudaStream_t st) {
     switch ((int)(p.M >> 12)) {
         case 16: return launch_cols_tpc_M1<16>(p, n_sm, st);
         case 32: return launch_cols_tpc_M1<32>(p, n_sm, st);
@@ -129,7 +153,7 @@ static cudaError_t launch_cols_tpc(const ColsTpcParams& p, const cd* tw, int n_s
         case 20: return launch_cols_tpc_M1<20>(p, n_sm, st);
         case 24: return launch_cols_tpc_M1<24>(p, n_sm, st);
         case 40: return launch_cols_tpc_M1<40>(p, n_sm, st);
-        case 512: return launch_cols_tpc2(p, tw, n_sm, st);
+        case 128: case 256: case 512: return launch_cols_tpc2(p, tw, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }

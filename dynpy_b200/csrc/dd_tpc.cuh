@@ -689,28 +689,52 @@ __global__ void __launch_bounds__(B * C, 384 / (B * C)) k_cols_tpc2(const ColsTp
 // series are formed from them.  The phase-A twiddles W_M1^{b c} are loop-invariant per thread: they come from a
 // 16 x B table in shared memory (the C column threads of one b read the same entry: one wavefront per warp
 // load) instead of a 14-product chain per series.
-template <int B, int C, int PER_SM>
-__global__ void __launch_bounds__(B * C, PER_SM) k_cols_tpc3(const ColsTpcParams p, const cd* __restrict__ twp) {
-    static_assert(B == 32, "phase A (B x C threads) and phase C (16 x 2 x C threads) use the same threads only for B = 32");
+// B = 16 (M1 = 256) and B = 8 (M1 = 128) run the same two phases with other thread roles: for B = 16 a phase-C thread
+// (c, column) does the whole 16-point transform over b (no parity split), 16 C threads in both phases; for B = 8 phase C
+// is a plain fft8 per (c, column) on 16 C threads and phase A, which has only 8 C (b, column) roles, is split over two
+// threads per role by output parity (one runs fft8 for the even c, the other fft8_odd for the odd c).
+template <int B, int C> struct Tpc3Shape {
+    static constexpr bool SPLIT_C = B == 32;            // phase C: B-point transform as two B/2-point codelets on two threads
+    static constexpr bool SPLIT_A = B == 8;             // phase A: even / odd c on two threads
+    static constexpr int NT = (B >= 16 ? B : 16) * C;
+    static constexpr int U = SPLIT_C ? B / 2 : B;       // points per phase-C thread
+    // row of the exchange buffer S[c][b][col]: B C entries + a pad of 4 (64 bytes) — with C = 4 the four c rows a
+    // phase-C warp reads at once are otherwise a multiple of 128 bytes apart (4-way bank conflict on every load)
+    static constexpr int SROW = B * C + (C == 4 ? 4 : 0);
+    static constexpr size_t smem_bytes(bool gs) {
+        return ((size_t)16 * SROW + 16 * B + (gs ? 16 * NT : 0)) * sizeof(cd);
+    }
+};
+// GS = true: the two geometry streams of a series group live in a thread-private shared-memory zone (16 entries per
+// thread, filled by cp.async) instead of 64 registers, which lets three CTAs per SM run without spills.
+template <int B, int C, int PER_SM, bool GS>
+__global__ void __launch_bounds__(Tpc3Shape<B, C>::NT, PER_SM) k_cols_tpc3(const ColsTpcParams p, const cd* __restrict__ twp) {
+    static_assert(B == 32 || B == 16 || B == 8, "column lengths 512, 256, 128");
+    using Shape = Tpc3Shape<B, C>;
     constexpr int M1 = 16 * B;
-    constexpr int HB = B / 2;
-    extern __shared__ double2 smem[];  // S[c][b][col] (16 * B * C entries), then TA[c][b] (16 * B entries)
-    cd* TA = smem + 16 * B * C;
+    constexpr int HB = Shape::U;
+    extern __shared__ double2 smem[];  // S[c][b][col] (16 rows of SROW entries), TA[c][b] (16 * B entries), ZG[2][8][NT]
+    constexpr int SROW = Shape::SROW;
+    cd* TA = smem + 16 * SROW;
+    cd* ZG = TA + 16 * B + threadIdx.x;   // GS: entry (stream s, sample a) at ZG[(8 s + a) * NT]
     const int tid = threadIdx.x;
     const i64 N = p.N;
     const int nfr = (int)(N < (i64)(M1 / 2) * 4096 ? N : (i64)(M1 / 2) * 4096);
-    const double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
-    const double KF = 1.5853309190424043;
+    constexpr double C20 = 0.31539156525252000603, C21 = -0.77254840404638362, C22 = 0.38627420202319181;
+    constexpr double KF = 1.5853309190424043;
     constexpr i64 TS = (i64)M1 * DYNPY_T_RS;
     const int tile = blockIdx.x;
-    const int colA = tid % C, bA = tid / C;
+    const int colA = tid % C, bA = (tid / C) % B, halfA = tid / (B * C);   // halfA: 0 unless SPLIT_A
     const int n2A = tile * C + colA;
-    const int colC = tid % C, par = (tid / C) & 1, cC = tid / (2 * C);
+    const int colC = tid % C;
+    const int par = Shape::SPLIT_C ? (tid / C) & 1 : 0;
+    const int cC = Shape::SPLIT_C ? tid / (2 * C) : tid / C;
     const int n2C = tile * C + colC;
     const double inv_M = 1.0 / (double)p.M;
+    constexpr int KSTEP = Shape::SPLIT_C ? 32 : 16;                          // k1 = c + 16 par + KSTEP d
     const cd seed = w_exact(((i64)n2C * (cC + 16 * par)) % p.M, inv_M);   // W_M^{n2 (c + 16 p)}
-    const cd step = w_exact(((i64)n2C * 32) % p.M, inv_M);                // W_M^{32 n2}
-    for (int e = tid; e < 16 * B; e += B * C) TA[e] = ldg_cd(twp + (e / B) * (e % B) * (4096 / M1));   // W_M1^{b c}
+    const cd step = w_exact(((i64)n2C * KSTEP) % p.M, inv_M);             // W_M^{KSTEP n2}
+    for (int e = tid; e < 16 * B; e += Shape::NT) TA[e] = ldg_cd(twp + (e / B) * (e % B) * (4096 / M1));   // W_M1^{b c}
     __syncthreads();
     // frames of this thread's residue: (B a + b) 4096 + n2, a = 0..7
     unsigned onmask = 0;
@@ -724,7 +748,9 @@ __global__ void __launch_bounds__(B * C, PER_SM) k_cols_tpc3(const ColsTpcParams
         const double mq = __ldg(p.rsum + 2 * item + 1) * p.inv_n;
         // series in three groups that share their two streams: complex series of p (streams 0, 1), of q (2, 3),
         // packed real series of p + i q (1, 3)
-        cd GA[8], GB[8];
+        cd GA[GS ? 1 : 8], GB[GS ? 1 : 8];
+        auto ga = [&](int a) -> cd { if constexpr (GS) return ZG[a * Shape::NT]; else return GA[a]; };
+        auto gb = [&](int a) -> cd { if constexpr (GS) return ZG[(8 + a) * Shape::NT]; else return GB[a]; };
 #pragma unroll 1
         for (int idx = 0; idx < 11; ++idx) {
             const int slot = idx < 8 ? ((idx & 3) == 0 ? 1 : (idx & 3) == 1 ? 3 : (idx & 3) == 2 ? 7 : 9) + (idx >> 2)
@@ -737,65 +763,110 @@ __global__ void __launch_bounds__(B * C, PER_SM) k_cols_tpc3(const ColsTpcParams
                     const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
                     const bool on = (onmask >> a) & 1u;
                     const cd zero = make_double2(0.0, 0.0);
-                    GA[a] = on ? ldg_cd(sa + fr) : zero;
-                    GB[a] = on ? ldg_cd(sb + fr) : zero;
+                    if constexpr (GS) {
+                        cp_async16_zfill(ZG + a * Shape::NT, sa + fr, on);
+                        cp_async16_zfill(ZG + (8 + a) * Shape::NT, sb + fr, on);
+                    } else {
+                        GA[a] = on ? ldg_cd(sa + fr) : zero;
+                        GB[a] = on ? ldg_cd(sb + fr) : zero;
+                    }
                 }
+                if constexpr (GS) asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             }
-            // ---- phase A: the 8 samples of residue b
+            // ---- phase A: the 8 samples of residue b, one specialised block per kind of series (the slot is uniform
+            // over the CTA).  Frames beyond the series and a missing second pair arrive as zero geometry, which makes
+            // every series with a factor x, y, z or r^-3 vanish; only Y20 and r^-3 - <r^-3> switch their constant off.
             cd v[8];
-            if (idx >= 8) {           // real series of p and q packed as re + i im; GA, GB = (z/r, r^-3) of p, q
-                const double c = slot == 5 ? 1.0 : (slot == 6 ? KF * C20 : C20);
+            auto form = [&](auto kind) {
+                constexpr int K = decltype(kind)::value;   // 0 Y20 | 5 r^-3 | 6 F20 | 1 Y21 | 3 Y22 | 7 F21 | 9 F22
+                if constexpr (K == 0 || K == 5 || K == 6) {   // GA, GB = (z/r, r^-3) of p, q -> re + i im
+                    const unsigned onq = q_exists ? onmask : 0u;
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const bool on = (onmask >> a) & 1u;
-                    const double yp = slot == 5 ? 1.0 : fma(3.0 * GA[a].x, GA[a].x, -1.0);
-                    const double yq = slot == 5 ? 1.0 : fma(3.0 * GB[a].x, GB[a].x, -1.0);
-                    const double sp = slot == 0 ? c : c * GA[a].y, sq = slot == 0 ? c : c * GB[a].y;
-                    v[a].x = on ? sp * yp - (slot == 5 ? mp : 0.0) : 0.0;
-                    v[a].y = (on && q_exists) ? sq * yq - (slot == 5 ? mq : 0.0) : 0.0;
-                }
-            } else {                  // GA = (x, y)/r, GB = (z/r, r^-3) of the series' pair
-                const bool weighted = slot >= 7;
-                const bool order1 = slot == 1 || slot == 2 || slot == 7 || slot == 8;
-                const double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
+                    for (int a = 0; a < 8; ++a) {
+                        if constexpr (K == 0) {
+                            const cd zp = ga(a), zq = gb(a);
+                            v[a].x = (((onmask >> a) & 1u) ? C20 : 0.0) * fma(3.0 * zp.x, zp.x, -1.0);
+                            v[a].y = (((onq >> a) & 1u) ? C20 : 0.0) * fma(3.0 * zq.x, zq.x, -1.0);
+                        } else if constexpr (K == 5) {
+                            v[a].x = ga(a).y - (((onmask >> a) & 1u) ? mp : 0.0);
+                            v[a].y = gb(a).y - (((onq >> a) & 1u) ? mq : 0.0);
+                        } else {
+                            const cd zp = ga(a), zq = gb(a);
+                            v[a].x = (KF * C20) * zp.y * fma(3.0 * zp.x, zp.x, -1.0);
+                            v[a].y = (KF * C20) * zq.y * fma(3.0 * zq.x, zq.x, -1.0);
+                        }
+                    }
+                } else {                  // GA = (x, y)/r, GB = (z/r, r^-3) of the series' pair
+                    constexpr bool weighted = K >= 7;
+                    constexpr bool order1 = K == 1 || K == 7;
+                    constexpr double c = (order1 ? C21 : C22) * (weighted ? KF : 1.0);
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const cd xy = GA[a], zr = GB[a];
-                    const cd w = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
-                    const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
-                    v[a] = make_double2(sc * w.x, sc * w.y);
+                    for (int a = 0; a < 8; ++a) {
+                        const cd xy = ga(a), zr = gb(a);
+                        const cd w = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
+                        const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
+                        v[a] = make_double2(sc * w.x, sc * w.y);
+                    }
                 }
+            };
+            switch (slot) {
+                case 0: form(TpcKind<0>{}); break;
+                case 5: form(TpcKind<5>{}); break;
+                case 6: form(TpcKind<6>{}); break;
+                case 1: case 2: form(TpcKind<1>{}); break;
+                case 3: case 4: form(TpcKind<3>{}); break;
+                case 7: case 8: form(TpcKind<7>{}); break;
+                default: form(TpcKind<9>{}); break;
             }
-            {
+            if constexpr (!Shape::SPLIT_A) {
                 cd e[8];
 #pragma unroll
                 for (int a = 0; a < 8; ++a) e[a] = v[a];
                 fft8(e);        // y[2 c']
                 fft8_odd(v);    // y[2 c' + 1]
-                smem[(0 * B + bA) * C + colA] = e[0];
+                smem[bA * C + colA] = e[0];
 #pragma unroll
                 for (int c = 1; c < 16; ++c) {
                     const cd y = (c & 1) ? v[c >> 1] : e[c >> 1];
-                    smem[(c * B + bA) * C + colA] = cmul(y, TA[c * B + bA]);
+                    smem[c * SROW + bA * C + colA] = cmul(y, TA[c * B + bA]);
                 }
+            } else if (halfA == 0) {
+                fft8(v);        // y[2 c']
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) smem[c * SROW + bA * C + colA] = c ? cmul(v[c >> 1], TA[c * B + bA]) : v[0];
+            } else {
+                fft8_odd(v);    // y[2 c' + 1]
+#pragma unroll
+                for (int c = 1; c < 16; c += 2) smem[c * SROW + bA * C + colA] = cmul(v[c >> 1], TA[c * B + bA]);
             }
             __syncthreads();
-            // ---- phase C: B-point transform over b for (c, column), parity `par`
+            // ---- phase C: B-point transform over b for (c, column)
             cd u[HB];
+            if constexpr (Shape::SPLIT_C) {   // parity `par`: sums / differences of the two halves, B/2-point codelet
 #pragma unroll
-            for (int j = 0; j < HB; ++j) {
-                const cd y0 = smem[(cC * B + j) * C + colC];
-                const cd y1 = smem[(cC * B + j + HB) * C + colC];
-                u[j] = par ? make_double2(y0.x - y1.x, y0.y - y1.y) : make_double2(y0.x + y1.x, y0.y + y1.y);
+                for (int j = 0; j < HB; ++j) {
+                    const cd y0 = smem[cC * SROW + j * C + colC];
+                    const cd y1 = smem[cC * SROW + (j + HB) * C + colC];
+                    u[j] = par ? make_double2(y0.x - y1.x, y0.y - y1.y) : make_double2(y0.x + y1.x, y0.y + y1.y);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < HB; ++j) u[j] = smem[cC * SROW + j * C + colC];
             }
             __syncthreads();   // the buffer may be rewritten by the next series
-            if (par) Tpc2Codelets<B>::odd(u); else Tpc2Codelets<B>::even(u);
+            if constexpr (Shape::SPLIT_C) {
+                if (par) Tpc2Codelets<B>::odd(u); else Tpc2Codelets<B>::even(u);
+            } else if constexpr (B == 16) {
+                fft16(u);
+            } else {
+                fft8(u);
+            }
             cd* dst = p.T + (item * 11 + slot) * TS + n2C;
             {
                 cd w = seed;
 #pragma unroll
                 for (int dd = 0; dd < HB; ++dd) {
-                    const int k1 = cC + 16 * (2 * dd + par);
+                    const int k1 = cC + 16 * par + KSTEP * dd;
                     st_stream(dst + (i64)k1 * DYNPY_T_RS, cmul(u[dd], w));
                     if (dd + 1 < HB) w = cmul(w, step);
                 }

@@ -27,6 +27,11 @@ namespace dynpy {
 #ifndef DYNPY_T_RS
 #define DYNPY_T_RS (4096 + 16)
 #endif
+// 1: the next row is loaded into 64 registers under step 3 of the current one; 0 (A/B): every row is read at the
+// top of its own iteration (out of L2, where the bulk prefetch put it), which frees those registers
+#ifndef DYNPY_ROWS_NX
+#define DYNPY_ROWS_NX 1
+#endif
 
 struct Rows2Params {
     const cd* T;            // [items][nslots][M1][rs]
@@ -122,14 +127,21 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     i64 item = cur.item;
     const cd* src = ptr_of(cur);
 
+#if DYNPY_ROWS_NX
     cd nx[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
+#endif
 
     for (i64 u = u0; u < u1; ++u) {
         cd v[16];
+#if DYNPY_ROWS_NX
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = nx[q];
+#else
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = ldcg_cd2(src + t_off(q));
+#endif
         if constexpr (FIX) {
             const double mr = p.rsum[2 * item] * p.inv_n, mi = p.rsum[2 * item + 1] * p.inv_n;
             const cd* rr = p.R + (i64)k1 * p.rs;
@@ -182,8 +194,10 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         // ---- step 3
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = smem[b3 + q];
+#if DYNPY_ROWS_NX
 #pragma unroll
         for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
+#endif
         __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten
         fft16(v);
 #pragma unroll
