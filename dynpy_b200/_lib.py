@@ -38,6 +38,7 @@ SIGNATURES = {
     "dynpy_supercell_f64": (i32, [p, i64, i64, i64, f64, p, p]),
     "dynpy_topology_check_f64": (i32, [p, i64, i64, p, f64, p, f64, f64, f64, f64, p, p]),
     "dynpy_topology_events_f64": (i32, [p, i64, i64, p, f64, p, f64, f64, f64, f64, p, i64, p, p]),
+    "dynpy_topology_events_range_f64": (i32, [p, i64, i64, i64, i64, p, f64, p, f64, f64, f64, f64, p, i64, p, p]),
     "dynpy_dd_pair_count_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, f64, p, p, p]),
     "dynpy_dd_workspace_bytes": (i64, [i64, i64, i64]),
     "dynpy_dd_pairs_to_spectrum_f64": (i32, [p, i64, i64, p, p, i64, f64, f64, f64, p, i64, p, i64, p]),

@@ -445,7 +445,7 @@ int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_fr
     if (rc) return rc;
     const unsigned long long init[2] = {0ull, ~0ull};
     DYNPY_CHECK(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st), "topology init");
-    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
+    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, 0, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
                                       (unsigned long long*)out, nullptr, 0, st), "topology check");
     return DYNPY_OK;
 }
@@ -453,9 +453,17 @@ int dynpy_topology_check_f64(const double* coords, int64_t n_atoms, int64_t n_fr
 int dynpy_topology_events_f64(const double* coords, int64_t n_atoms, int64_t n_frames, const double* rcov,
                               double bond_extra, const uint8_t* expect, double a, double b, double c, double dmax,
                               int64_t* events, int64_t capacity, uint64_t* out, dynpy_stream_t stream) {
+    return dynpy_topology_events_range_f64(coords, n_atoms, n_frames, 0, n_frames, rcov, bond_extra, expect, a, b, c,
+                                           dmax, events, capacity, out, stream);
+}
+
+int dynpy_topology_events_range_f64(const double* coords, int64_t n_atoms, int64_t n_frames, int64_t frame_begin,
+                                    int64_t frame_end, const double* rcov, double bond_extra, const uint8_t* expect,
+                                    double a, double b, double c, double dmax, int64_t* events, int64_t capacity,
+                                    uint64_t* out, dynpy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!coords || !rcov || !expect || !out || !events || capacity < 1 || n_atoms < 1 || n_frames < 1 ||
-        n_atoms > 65535) {
+        n_atoms > 65535 || frame_begin < 0 || frame_end > n_frames || frame_begin > frame_end) {
         set_error("dynpy_topology_events_f64: invalid arguments");
         return DYNPY_ERR_INVALID;
     }
@@ -464,8 +472,8 @@ int dynpy_topology_events_f64(const double* coords, int64_t n_atoms, int64_t n_f
     if (rc) return rc;
     const unsigned long long init[3] = {0ull, ~0ull, 0ull};
     DYNPY_CHECK(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st), "topology init");
-    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, rcov, bond_extra, expect, a, b, c, dmax,
-                                      (unsigned long long*)out, (i64*)events, capacity, st), "topology events");
+    DYNPY_CHECK(launch_topology_check(coords, n_atoms, n_frames, frame_begin, frame_end, rcov, bond_extra, expect, a, b,
+                                      c, dmax, (unsigned long long*)out, (i64*)events, capacity, st), "topology events");
     return DYNPY_OK;
 }
 

@@ -25,7 +25,7 @@ cudaError_t launch_cart_to_dipolar(const double* dx, const double* dy, const dou
                                    double* out, int n_sm, cudaStream_t st);
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
                                  double b, double c, double rmax, i64* counts, int* frame_hit, cudaStream_t st);
-cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
+cudaError_t launch_topology_check(const double* X, i64 A, i64 N, i64 n0, i64 n1, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
                                   unsigned long long* out, i64* events, i64 cap, cudaStream_t st);
 cudaError_t launch_dd_ragged_words(const double* X, i64 N, i64 NC, const int* pi, const int* pj, i64 pair0, i64 npairs,

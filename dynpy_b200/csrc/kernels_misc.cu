@@ -286,12 +286,12 @@ __global__ void __launch_bounds__(TOPO_NT)
 k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
                  const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
                  const double* __restrict__ Tscreen, i64 tiles, unsigned long long* __restrict__ out,
-                 i64* __restrict__ events, i64 cap) {
+                 i64* __restrict__ events, i64 cap, i64 n0, i64 n1) {
     __shared__ int s_nb;
     __shared__ unsigned s_bond[TOPO_BCAP];   // (k << 24) | j : expected bonds (i0 + k, j), j > i0 + k
     // 1-D grid, atom tiles fastest: the CTAs of one frame chunk are adjacent and share its coordinates in L2
     const i64 chunk = blockIdx.x / tiles;
-    const i64 n = chunk * TOPO_NT + threadIdx.x;
+    const i64 n = n0 + chunk * TOPO_NT + threadIdx.x;   // frames [n0, n1) of the N the arrays hold
     const i64 i0 = (blockIdx.x - chunk * tiles) * TOPO_TI;
     const double T = *Tscreen;
     const double ha = 0.5 * a, hb = 0.5 * b, hc = 0.5 * c;
@@ -310,7 +310,7 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
     __syncthreads();
     const int nb = s_nb;
     const bool listed = nb <= TOPO_BCAP && A < (1 << 24);   // else: expected flags are read from global memory
-    if (n >= N) return;
+    if (n >= n1) return;
     unsigned long long bad = 0;
     auto report = [&](i64 i, i64 j) {
         ++bad;
@@ -381,18 +381,18 @@ __global__ void k_topo_screen_radius(const double* __restrict__ rcov, i64 n, dou
         *out = T * (1.0 + 1e-9) + 1e-9;
     }
 }
-cudaError_t launch_topology_check(const double* X, i64 A, i64 N, const double* rcov, double extra,
+cudaError_t launch_topology_check(const double* X, i64 A, i64 N, i64 n0, i64 n1, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
                                   unsigned long long* out, i64* events, i64 cap, cudaStream_t st) {
-    if (A < 2 || N < 1) return cudaSuccess;
-    const i64 tiles = (A + TOPO_TI - 1) / TOPO_TI, chunks = (N + TOPO_NT - 1) / TOPO_NT;
+    if (A < 2 || N < 1 || n1 <= n0) return cudaSuccess;
+    const i64 tiles = (A + TOPO_TI - 1) / TOPO_TI, chunks = (n1 - n0 + TOPO_NT - 1) / TOPO_NT;
     if (tiles * chunks > 0x7fffffffll) return cudaErrorInvalidValue;
     double* T = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&T, sizeof(double), st);
     if (e != cudaSuccess) return e;
     k_topo_screen_radius<<<1, 256, 0, st>>>(rcov, A, extra, dmax, T);
     k_topology_check<<<(unsigned)(tiles * chunks), TOPO_NT, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax,
-                                                                      T, tiles, out, events, cap);
+                                                                      T, tiles, out, events, cap, n0, n1);
     e = cudaGetLastError();
     cudaFreeAsync(T, st);   // stream-ordered: released after the kernel above has run
     return e;

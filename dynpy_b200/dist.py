@@ -102,6 +102,15 @@ def broadcast_object(obj, src: int = 0):
     return obj
 
 
+def all_gather_object(obj) -> list:
+    """The python objects of all ranks, in rank order (single process: [obj])."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, obj)
+        return parts
+    return [obj]
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

@@ -251,9 +251,10 @@ def topology_check(coords, rcov, bond_extra, expect, cell, dmax):
     return int(bad), (int(first) if bad else -1)
 
 
-def topology_events(coords, rcov, bond_extra, expect, cell, dmax, capacity=1 << 16):
+def topology_events(coords, rcov, bond_extra, expect, cell, dmax, capacity=1 << 16, frames=None):
     """Pair-frames whose bond flag differs from `expect`: int64 array [k, 3] of (frame index, i, j), host.
-    Raises when more than `capacity` differ (a trajectory that reactive is outside the static-topology design)."""
+    Raises when more than `capacity` differ (a trajectory that reactive is outside the static-topology design).
+    frames = (begin, end): scan only that block of frames (one block per rank, the host merges the lists)."""
     lib = _lib.load()
     coords = _chk(coords, torch.float64, "coords")
     rcov = _chk(rcov, torch.float64, "rcov")
@@ -262,16 +263,20 @@ def topology_events(coords, rcov, bond_extra, expect, cell, dmax, capacity=1 << 
     out = torch.zeros(3, dtype=torch.int64, device=coords.device)
     ev = torch.empty((capacity, 3), dtype=torch.int64, device=coords.device)
     with torch.cuda.device(coords.device):
-        rc = lib.dynpy_topology_events_f64(coords.data_ptr(), A, F, rcov.data_ptr(), float(bond_extra), expect.data_ptr(),
-                                           float(cell[0]), float(cell[1]), float(cell[2]), float(dmax), ev.data_ptr(),
-                                           int(capacity), out.data_ptr(), _stream())
-    _lib.check(rc, "dynpy_topology_events_f64")
+        f0, f1 = (0, F) if frames is None else (int(frames[0]), int(frames[1]))
+        rc = lib.dynpy_topology_events_range_f64(coords.data_ptr(), A, F, f0, f1, rcov.data_ptr(), float(bond_extra),
+                                                 expect.data_ptr(), float(cell[0]), float(cell[1]), float(cell[2]),
+                                                 float(dmax), ev.data_ptr(), int(capacity), out.data_ptr(), _stream())
+    _lib.check(rc, "dynpy_topology_events_range_f64")
     bad, first, n = out.tolist()
     if n > capacity:
         raise _lib.DynpyError("bond topology differs from the indexing frame in %d pair-frames (> %d): too reactive for "
                               "the static-topology indexing" % (n, capacity))
-    e = ev[:n].cpu().numpy()
-    return e[np.lexsort((e[:, 2], e[:, 1], e[:, 0]))] if n else e
+    if n == 0:
+        return ev[:0].cpu().numpy()
+    e = ev[:n]
+    order = torch.argsort(e[:, 0] * (A * A) + e[:, 1] * A + e[:, 2])   # (frame, i, j) order, sorted on the device
+    return e[order].cpu().numpy()
 
 
 def dd_pair_count(coords, pair_i, pair_j, cell, rmax, frame_hit=None):

@@ -231,8 +231,58 @@ class FrameTopologies:
         return out
 
 
+class _LazyPairs(dict):
+    """{frame: [(i, j), ...]} over an event array sorted by frame: the per-frame lists are cut out on first access
+    (a reactive synthetic box has ~1e6 events; a run that never looks at them — pair_type 'all' — pays nothing)."""
+
+    def __init__(self, ev: np.ndarray):
+        super().__init__()
+        frames, first = np.unique(ev[:, 0], return_index=True) if len(ev) else (np.empty(0, np.int64), np.empty(0, np.int64))
+        self._ev = ev
+        self._span = dict(zip(frames.tolist(), zip(first.tolist(), np.append(first[1:], len(ev)).tolist())))
+
+    def __len__(self):
+        return len(self._span)
+
+    def __bool__(self):
+        return bool(self._span)
+
+    def __contains__(self, f):
+        return f in self._span
+
+    def __iter__(self):
+        return iter(self._span)
+
+    def keys(self):
+        return self._span.keys()
+
+    def __missing__(self, f):
+        a, b = self._span[f]
+        v = [(int(i), int(j)) for i, j in self._ev[a:b, 1:3]]
+        self[f] = v
+        return v
+
+    def __getitem__(self, f):
+        if not dict.__contains__(self, f):
+            return self.__missing__(f)
+        return dict.__getitem__(self, f)
+
+    def items(self):
+        return ((f, self[f]) for f in self._span)
+
+    def values(self):
+        return (self[f] for f in self._span)
+
+
+def _group_events(ev: np.ndarray):
+    """(frame, i, j) rows -> {frame: [(i, j), ...]} (rows sorted by frame first)."""
+    if len(ev) and np.any(np.diff(ev[:, 0]) < 0):
+        ev = ev[np.lexsort((ev[:, 2], ev[:, 1], ev[:, 0]))]
+    return _LazyPairs(ev)
+
+
 def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra: float = 0.45,
-                   check_frames=None, dynamic: bool = False):
+                   check_frames=None, dynamic: bool = False, capacity: int = 1 << 16):
     """Topology from frame 0, verified on every frame by the device scan.
 
     dynamic=False: a bond list that changes along the trajectory raises (the dipolar path indexes pairs from a
@@ -248,11 +298,18 @@ def build_topology(wrapped: torch.Tensor, symbols, cell, dmax: float, bond_extra
         expect[torch.from_numpy(two0["i"][b0]), torch.from_numpy(two0["j"][b0])] = 1
         rc = torch.tensor([SYM2COVRAD[s] for s in symbols], dtype=torch.float64, device=wrapped.device)
         if dynamic:
-            ev = ops.topology_events(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
-            changes = {}
-            for f, i, j in ev.tolist():
-                changes.setdefault(f, []).append((i, j))
-            return FrameTopologies(topo, changes, F), two0
+            # several ranks (every rank holds the whole trajectory): each scans its block of frames, the lists are merged
+            from . import dist
+            rank, world = dist.rank_world()
+            if world > 1:
+                lo, hi = dist.shard_range(F, rank, world)
+                mine = ops.topology_events(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax, capacity,
+                                           frames=(lo, hi))
+                parts = dist.all_gather_object(mine)
+                ev = np.concatenate([p for p in parts if len(p)] or [mine])
+            else:
+                ev = ops.topology_events(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax, capacity)
+            return FrameTopologies(topo, _group_events(ev), F), two0
         bad, first = ops.topology_check(wrapped, rc, bond_extra, expect.to(wrapped.device), cell, dmax)
         if bad:
             raise RuntimeError("bond topology changes along the trajectory (%d pair-frames differ from frame index 0, "

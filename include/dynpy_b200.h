@@ -149,6 +149,15 @@ int dynpy_topology_events_f64(const double* coords, int64_t n_atoms, int64_t n_f
                               double b, double c, double dmax, int64_t* events, int64_t capacity,
                               uint64_t* out, dynpy_stream_t stream);
 
+/* The same scan over the frames [frame_begin, frame_end) only (events carry absolute frame indices): one process
+ * per GPU scans its block of frames and the host merges the lists (the scan is O(atoms^2 x frames) and would
+ * otherwise be repeated on every rank).  Reference: universe.py:411-451 over all frames. */
+int dynpy_topology_events_range_f64(const double* coords, int64_t n_atoms, int64_t n_frames,
+                                    int64_t frame_begin, int64_t frame_end, const double* rcov,
+                                    double bond_extra, const uint8_t* expect, double a, double b, double c,
+                                    double dmax, int64_t* events, int64_t capacity, uint64_t* out,
+                                    dynpy_stream_t stream);
+
 /* frames in which each pair's minimum-image distance is < rmax  (the presence rule of
  * compute_atom_two, DDparse.py:148): counts[p] in [0, n_frames]. coords are WRAPPED.
  * frame_hit (optional, [n_frames], caller-zeroed) is set to 1 where any pair is present. */
