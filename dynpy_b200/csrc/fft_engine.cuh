@@ -21,6 +21,7 @@
 //
 // Bandwidth/FLOP accounting per kernel is in DESIGN.md §kernels.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -268,6 +269,25 @@ struct QrLoader {
     }
     __device__ __forceinline__ cd raw(const Ctx& c, i64 n) const { return load(c, n); }
     __device__ __forceinline__ cd finish(const Ctx& c, cd v) const { return v; }
+    // The same sample with the kind of series fixed at compile time (the slot is uniform over a CTA: the column
+    // kernel branches once per series instead of once per sample).  K = 0: k20 (Vzz_a + i Vzz_b); K = 1: R2,+-1 =
+    // Vxz - i Vyz; K = 2: R2,+-2 = (Vxx - Vyy) / 2 - i Vxy, of nucleus p (nullptr: the missing second nucleus).
+    template <int K>
+    __device__ __forceinline__ cd load_kind(const Ctx& c, const double* p, i64 n) const {
+        cd v = make_double2(0.0, 0.0);
+        if (n < N) {
+            if constexpr (K == 0) {
+                const double k20 = 1.2247448713915889;
+                v.x = k20 * __ldg(c.a + 2 * N + n);
+                if (c.b) v.y = k20 * __ldg(c.b + 2 * N + n);
+            } else if constexpr (K == 1) {
+                if (p) v = make_double2(__ldg(p + 4 * N + n), -__ldg(p + 5 * N + n));
+            } else {
+                if (p) v = make_double2(0.5 * (__ldg(p + n) - __ldg(p + N + n)), -__ldg(p + 3 * N + n));
+            }
+        }
+        return v;
+    }
 };
 
 // Final transform: reads the accumulated spectrum S' (internal order) of accumulator f as a
@@ -611,7 +631,24 @@ __global__ void __launch_bounds__(256, 2) k_cols_tpcg(Loader ld, cd* __restrict_
 #pragma unroll 1
         for (int par = 0; par < 2; ++par) {
             cd v[H];
-            if (Loader::DENSE || par == 0) {
+            if constexpr (std::is_same<Loader, QrLoader>::value) {
+                if (par == 0) {
+                    const double* pn = (ctx.slot <= 2) ? ctx.a : ctx.b;
+                    auto fill = [&](auto kind) {
+                        constexpr int K = decltype(kind)::value;
+#pragma unroll
+                        for (int j = 0; j < H; ++j) v[j] = ld.template load_kind<K>(ctx, pn, (i64)j * M2 + n2);
+                    };
+                    if (ctx.slot == 0) fill(std::integral_constant<int, 0>{});
+                    else if (ctx.slot & 1) fill(std::integral_constant<int, 1>{});
+                    else fill(std::integral_constant<int, 2>{});
+#pragma unroll
+                    for (int j = 0; j < H; ++j) stash[j * 256] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) v[j] = stash[j * 256];
+                }
+            } else if (Loader::DENSE || par == 0) {
 #pragma unroll
                 for (int j = 0; j < H; ++j) v[j] = ld.raw(ctx, (i64)j * M2 + n2);
 #pragma unroll

@@ -667,7 +667,7 @@ cudaError_t launch_spectrum_even_natural(const double* in, double* out, i64 n_sp
 // ------------------------------------------------------------------ spin-rotation
 __device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3], double x[3]) {
     // Gaussian elimination with partial pivoting (what numpy.linalg.solve / LAPACK gesv does)
-    double A[3][3], b[3];
+    double A[3][3], b[3], ipiv[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { b[i] = b_[i];
 #pragma unroll
@@ -684,19 +684,20 @@ __device__ __forceinline__ void solve3(const double A_[3][3], const double b_[3]
             for (int j = 0; j < 3; ++j) { double t = A[k][j]; A[k][j] = A[i][j]; A[i][j] = t; }
             double t = b[k]; b[k] = b[i]; b[i] = t;
         }
-#pragma unroll
-        const double ipiv = 1.0 / A[k][k];
+        ipiv[k] = 1.0 / A[k][k];
 #pragma unroll
         for (int i = k + 1; i < 3; ++i) {
-            const double l = A[i][k] * ipiv;
+            const double l = A[i][k] * ipiv[k];
 #pragma unroll
             for (int j = 0; j < 3; ++j) if (j >= k) A[i][j] -= l * A[k][j];
             b[i] -= l * b[k];
         }
     }
-    x[2] = b[2] / A[2][2];
-    x[1] = (b[1] - A[1][2] * x[2]) / A[1][1];
-    x[0] = (b[0] - A[0][1] * x[1] - A[0][2] * x[2]) / A[0][0];
+    // back substitution with the reciprocals of the pivots already at hand (three divisions fewer; one rounding of
+    // difference to b / A, far inside the tolerance: this kernel is bound by fp64 issue)
+    x[2] = b[2] * ipiv[2];
+    x[1] = (b[1] - A[1][2] * x[2]) * ipiv[1];
+    x[0] = (b[0] - A[0][1] * x[1] - A[0][2] * x[2]) * ipiv[0];
 }
 __device__ __forceinline__ void inv3(const double m[3][3], double o[3][3]) {
     const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1];
@@ -731,8 +732,9 @@ template <int NAT>
 __global__ void __launch_bounds__(128)
 k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 N, const int* __restrict__ mol_atoms,
             i64 n_mol, int nat_rt, const double* __restrict__ mass, const int* __restrict__ axis_atoms, int axis_rule,
-            double ca, double cb, double cc, double inv_dt, i64 n_out, double* __restrict__ J,
-            double* __restrict__ omega, double* __restrict__ axes) {
+            double ca, double cb, double cc, double ica, double icb, double icc,
+            const double* __restrict__ inv_msum, double inv_dt,
+            i64 n_out, double* __restrict__ J, double* __restrict__ omega, double* __restrict__ axes) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 m = blockIdx.y;
     if (t >= n_out) return;
@@ -772,7 +774,7 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
             for (int d = 0; d < 3; ++d) { cp[d] += mk * x[d]; cv[d] += mk * v[d]; }
         }
     }
-    const double im = 1.0 / msum;
+    const double im = __ldg(inv_msum);   // the per-slot masses are the same for every molecule: 1 / sum, formed once
 #pragma unroll
     for (int d = 0; d < 3; ++d) { cp[d] *= im; cv[d] *= im; }
     double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rv[3] = {0, 0, 0};
@@ -810,7 +812,7 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
     // kernel is bound by fp64 issue, not by HBM).
     const int* ax4 = axis_atoms + m * 4;
     const double cell[3] = {ca, cb, cc};
-    const double icell[3] = {1.0 / ca, 1.0 / cb, 1.0 / cc};
+    const double icell[3] = {ica, icb, icc};
     double dvec[2][3];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -858,17 +860,27 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
             for (int j = 0; j < 3; ++j) axes[(m * 9 + i * 3 + j) * n_out + t] = ax[i][j];
     }
 }
+__global__ void k_sr_inv_msum(const double* __restrict__ mass, int nat, double* __restrict__ out) {
+    double s = 0.0;
+    for (int k = 0; k < nat; ++k) s += mass[k];   // the same order of additions as the kernel's own sum
+    *out = 1.0 / s;
+}
 cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const int* mol_atoms, i64 n_mol, int nat,
                              const double* mass, const int* axis_atoms, int axis_rule, double a, double b, double c,
                              double inv_dt, double* J, double* omega, double* axes, cudaStream_t st) {
     const i64 n_out = vel ? N : N - 1;
     if (n_out <= 0 || n_mol <= 0) return cudaSuccess;
+    double* inv_msum = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&inv_msum, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    k_sr_inv_msum<<<1, 1, 0, st>>>(mass, nat, inv_msum);
     for (i64 m0 = 0; m0 < n_mol; m0 += 65535) {
         i64 cnt = n_mol - m0 < 65535 ? n_mol - m0 : 65535;
         dim3 grid((unsigned)((n_out + 127) / 128), (unsigned)cnt);
 #define SR_LAUNCH(NATC)                                                                                             \
     k_sr_angmom<NATC><<<grid, 128, 0, st>>>(pos, vel, N, mol_atoms + m0 * nat, cnt, nat, mass, axis_atoms + m0 * 4,   \
-                                            axis_rule, a, b, c, inv_dt, n_out, J ? J + m0 * 3 * n_out : nullptr,       \
+                                            axis_rule, a, b, c, 1.0 / a, 1.0 / b, 1.0 / c, inv_msum, inv_dt, n_out,         \
+                                            J ? J + m0 * 3 * n_out : nullptr,                                           \
                                             omega ? omega + m0 * 3 * n_out : nullptr,                                   \
                                             axes ? axes + m0 * 9 * n_out : nullptr)
         switch (nat) {  // water, methyl / ammonia-like, methane, acetonitrile; anything else: run-time loop
@@ -880,7 +892,9 @@ cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const 
         }
 #undef SR_LAUNCH
     }
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    cudaFreeAsync(inv_msum, st);   // stream-ordered: released after the kernels above have run
+    return e;
 }
 
 // ------------------------------------------------------------------ Simpson
