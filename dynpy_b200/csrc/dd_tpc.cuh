@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         const i64 item = ic / NCB;
         const bool live = !RAGGED || n2 < 4096;   // threads past the last column run on zeros and store nothing
         const cd w1 = ldg_cd(p.seeds + 2 * (n2 & 4095)), w2 = ldg_cd(p.seeds + 2 * (n2 & 4095) + 1);
-        cd* dst = p.T + (item * nslots + slot) * TS + n2;
+        cd* dst = p.T + (T_ITEM(item) * nslots + slot) * TS + n2;
         // slot -> series (kernels.h): 0 Y20 p+iq | 1,2 Y21 p,q | 3,4 Y22 p,q | 5 r^-3 p+iq | 6 F20 p+iq | 7,8 F21 p,q | 9,10 F22 p,q
         const int jlim = (nfr > n2 && live) ? (nfr - n2 + 4095) >> 12 : 0;
         if (p.sync_units) __syncthreads();  // re-align the warps of the CTA on the same code (instruction-cache locality)

@@ -33,6 +33,14 @@ namespace dynpy {
 #define DYNPY_ROWS_NX 1
 #endif
 
+// timing experiment only (results are garbage): the T addresses of all items folded onto DYNPY_T_ALIAS items, so that
+// T stays resident in L2 — measures what the two transform kernels would gain if T never went to DRAM
+#ifdef DYNPY_T_ALIAS
+#define T_ITEM(it) ((it) % (i64)DYNPY_T_ALIAS)
+#else
+#define T_ITEM(it) (it)
+#endif
+
 struct Rows2Params {
     const cd* T;            // [items][nslots][M1][rs]
     double* S;              // [nacc][M] accumulated |X|^2, internal order k1*4096 + k2
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     };
     auto slot_of = [&](const Cursor& c) -> int { return (int)((p.sel_pack >> (4 * c.si)) & 15ull); };
     auto ptr_of = [&](const Cursor& c) -> const cd* {
-        return p.T + ((c.item * p.nslots + slot_of(c)) * p.M1 + c.k1) * (i64)p.rs;
+        return p.T + ((T_ITEM(c.item) * p.nslots + slot_of(c)) * p.M1 + c.k1) * (i64)p.rs;
     };
     auto flush = [&](int slot, int k1) {
         double* sr = reinterpret_cast<double*>(smem);

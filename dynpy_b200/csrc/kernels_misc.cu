@@ -285,20 +285,33 @@ __device__ __forceinline__ bool topo_axis_near(double xi, double xj, double h, d
 __global__ void __launch_bounds__(TOPO_NT)
 k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
                  const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
-                 const double* __restrict__ Tscreen, i64 tiles, unsigned long long* __restrict__ out,
+                 double dmax, i64 tiles, unsigned long long* __restrict__ out,
                  i64* __restrict__ events, i64 cap, i64 n0, i64 n1) {
     __shared__ int s_nb;
+    __shared__ double s_rmax[TOPO_NT / 32];
     __shared__ unsigned s_bond[TOPO_BCAP];   // (k << 24) | j : expected bonds (i0 + k, j), j > i0 + k
     // 1-D grid, atom tiles fastest: the CTAs of one frame chunk are adjacent and share its coordinates in L2
     const i64 chunk = blockIdx.x / tiles;
     const i64 n = n0 + chunk * TOPO_NT + threadIdx.x;   // frames [n0, n1) of the N the arrays hold
     const i64 i0 = (blockIdx.x - chunk * tiles) * TOPO_TI;
-    const double T = *Tscreen;
-    const double ha = 0.5 * a, hb = 0.5 * b, hc = 0.5 * c;
-    const double ta = ha - T, tb = hb - T, tc = hc - T;
     const int ti = (int)(A - i0 < TOPO_TI ? A - i0 : TOPO_TI);
+    // screening radius: the largest bond threshold any pair can have (2 max rcov + extra, never more than dmax), with
+    // a margin that covers the rounding of the screen's own subtractions; formed per CTA (A loads, against the
+    // ~A * TOPO_TI * TOPO_NT pair-frames the CTA screens)
+    double rm = 0.0;
+    for (i64 k = threadIdx.x; k < A; k += TOPO_NT) rm = fmax(rm, __ldg(rcov + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+    if ((threadIdx.x & 31) == 0) s_rmax[threadIdx.x >> 5] = rm;
     if (threadIdx.x == 0) s_nb = 0;
     __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TOPO_NT / 32; ++w) rm = fmax(rm, s_rmax[w]);
+    double T = fmin(2.0 * rm + extra, dmax);
+    if (!(T > 0.0)) T = 0.0;
+    T = T * (1.0 + 1e-9) + 1e-9;
+    const double ha = 0.5 * a, hb = 0.5 * b, hc = 0.5 * c;
+    const double ta = ha - T, tb = hb - T, tc = hc - T;
     for (int k = 0; k < ti; ++k) {
         const unsigned char* row = expect + (i0 + k) * A;
         for (i64 j = i0 + k + 1 + threadIdx.x; j < A; j += TOPO_NT)
@@ -363,39 +376,15 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
         atomicMin(out + 1, (unsigned long long)n);
     }
 }
-// screening radius of k_topology_check: the largest bond threshold any pair can have (2 max rcov + extra, never
-// more than dmax), with a margin that covers the rounding of the screen's own subtractions
-__global__ void k_topo_screen_radius(const double* __restrict__ rcov, i64 n, double extra, double dmax,
-                                     double* __restrict__ out) {
-    double m = 0.0;
-    for (i64 k = threadIdx.x; k < n; k += blockDim.x) m = fmax(m, rcov[k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
-    __shared__ double sh[32];
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
-        double T = fmin(2.0 * m + extra, dmax);
-        if (!(T > 0.0)) T = 0.0;
-        *out = T * (1.0 + 1e-9) + 1e-9;
-    }
-}
 cudaError_t launch_topology_check(const double* X, i64 A, i64 N, i64 n0, i64 n1, const double* rcov, double extra,
                                   const unsigned char* expect, double a, double b, double c, double dmax,
                                   unsigned long long* out, i64* events, i64 cap, cudaStream_t st) {
     if (A < 2 || N < 1 || n1 <= n0) return cudaSuccess;
     const i64 tiles = (A + TOPO_TI - 1) / TOPO_TI, chunks = (n1 - n0 + TOPO_NT - 1) / TOPO_NT;
     if (tiles * chunks > 0x7fffffffll) return cudaErrorInvalidValue;
-    double* T = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&T, sizeof(double), st);
-    if (e != cudaSuccess) return e;
-    k_topo_screen_radius<<<1, 256, 0, st>>>(rcov, A, extra, dmax, T);
     k_topology_check<<<(unsigned)(tiles * chunks), TOPO_NT, 0, st>>>(X, A, N, rcov, extra, expect, a, b, c, dmax * dmax,
-                                                                      T, tiles, out, events, cap, n0, n1);
-    e = cudaGetLastError();
-    cudaFreeAsync(T, st);   // stream-ordered: released after the kernel above has run
-    return e;
+                                                                      dmax, tiles, out, events, cap, n0, n1);
+    return cudaGetLastError();
 }
 
 // ddrax.cart_to_dipolar_from_df (ddrax.py:110-126) as a stand-alone call: pair vectors -> the 11 real words
@@ -732,14 +721,22 @@ template <int NAT>
 __global__ void __launch_bounds__(128)
 k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 N, const int* __restrict__ mol_atoms,
             i64 n_mol, int nat_rt, const double* __restrict__ mass, const int* __restrict__ axis_atoms, int axis_rule,
-            double ca, double cb, double cc, double ica, double icb, double icc,
-            const double* __restrict__ inv_msum, double inv_dt,
+            double ca, double cb, double cc, double ica, double icb, double icc, double inv_dt,
             i64 n_out, double* __restrict__ J, double* __restrict__ omega, double* __restrict__ axes) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 m = blockIdx.y;
+    const int nat = NAT > 0 ? NAT : nat_rt;
+    // the per-slot masses are the same for every molecule: 1 / sum formed by one thread per CTA (one division
+    // instead of 128; the additions run in the order of the per-thread sum)
+    __shared__ double s_inv_msum;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nat; ++k) s += __ldg(mass + k);
+        s_inv_msum = 1.0 / s;
+    }
+    __syncthreads();
     if (t >= n_out) return;
     const i64 fr = vel ? t : t + 1;  // frame whose positions are used
-    const int nat = NAT > 0 ? NAT : nat_rt;
     const int* at = mol_atoms + m * nat;
     constexpr int NR = NAT > 0 ? NAT : 1;
     double rx[NR][3], vx[NR][3], mk_[NR];
@@ -774,7 +771,7 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
             for (int d = 0; d < 3; ++d) { cp[d] += mk * x[d]; cv[d] += mk * v[d]; }
         }
     }
-    const double im = __ldg(inv_msum);   // the per-slot masses are the same for every molecule: 1 / sum, formed once
+    const double im = s_inv_msum;
 #pragma unroll
     for (int d = 0; d < 3; ++d) { cp[d] *= im; cv[d] *= im; }
     double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rv[3] = {0, 0, 0};
@@ -860,26 +857,17 @@ k_sr_angmom(const double* __restrict__ pos, const double* __restrict__ vel, i64 
             for (int j = 0; j < 3; ++j) axes[(m * 9 + i * 3 + j) * n_out + t] = ax[i][j];
     }
 }
-__global__ void k_sr_inv_msum(const double* __restrict__ mass, int nat, double* __restrict__ out) {
-    double s = 0.0;
-    for (int k = 0; k < nat; ++k) s += mass[k];   // the same order of additions as the kernel's own sum
-    *out = 1.0 / s;
-}
 cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const int* mol_atoms, i64 n_mol, int nat,
                              const double* mass, const int* axis_atoms, int axis_rule, double a, double b, double c,
                              double inv_dt, double* J, double* omega, double* axes, cudaStream_t st) {
     const i64 n_out = vel ? N : N - 1;
     if (n_out <= 0 || n_mol <= 0) return cudaSuccess;
-    double* inv_msum = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&inv_msum, sizeof(double), st);
-    if (e != cudaSuccess) return e;
-    k_sr_inv_msum<<<1, 1, 0, st>>>(mass, nat, inv_msum);
     for (i64 m0 = 0; m0 < n_mol; m0 += 65535) {
         i64 cnt = n_mol - m0 < 65535 ? n_mol - m0 : 65535;
         dim3 grid((unsigned)((n_out + 127) / 128), (unsigned)cnt);
 #define SR_LAUNCH(NATC)                                                                                             \
     k_sr_angmom<NATC><<<grid, 128, 0, st>>>(pos, vel, N, mol_atoms + m0 * nat, cnt, nat, mass, axis_atoms + m0 * 4,   \
-                                            axis_rule, a, b, c, 1.0 / a, 1.0 / b, 1.0 / c, inv_msum, inv_dt, n_out,         \
+                                            axis_rule, a, b, c, 1.0 / a, 1.0 / b, 1.0 / c, inv_dt, n_out,                   \
                                             J ? J + m0 * 3 * n_out : nullptr,                                           \
                                             omega ? omega + m0 * 3 * n_out : nullptr,                                   \
                                             axes ? axes + m0 * 9 * n_out : nullptr)
@@ -892,9 +880,7 @@ cudaError_t launch_sr_angmom(const double* pos, const double* vel, i64 N, const 
         }
 #undef SR_LAUNCH
     }
-    e = cudaGetLastError();
-    cudaFreeAsync(inv_msum, st);   // stream-ordered: released after the kernels above have run
-    return e;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ Simpson
