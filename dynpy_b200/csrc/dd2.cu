@@ -130,6 +130,39 @@ cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int 
     return cudaGetLastError();
 }
 
+// 4096-point rows with a write epilogue (fft_engine.cuh EpiMode 1..3) through the same row kernel: T holds
+// transforms f_base .. f_base + n - 1, one after the other
+cudaError_t launch_rows2_write(Rows2Params p, int mode, int n_sm, cudaStream_t st) {
+    const size_t smem_row = (size_t)(pad16(4096) + 256) * sizeof(cd);
+    const size_t smem = mode == ROWS2_WRITE_POWER ? smem_row + (size_t)pad16(4096) * sizeof(double) : smem_row;
+    const i64 units = (i64)p.M1 * p.items;
+    if (units <= 0) return cudaSuccess;
+    p.nsel = 1;
+    p.sel_pack = 0;
+    p.nslots = 1;
+    {
+        static int pf = -1;
+        if (pf < 0) { const char* e = getenv("DYNPY_ROWS_PF"); pf = e ? atoi(e) : 1; }
+        p.pf_dist = pf;
+    }
+    int grid = 2 * n_sm;
+    if (grid > units) grid = (int)units;
+    ProfScope prof(PROF_ROWS, st);
+    cudaError_t e;
+#define ROWS2_WRITE_CASE(MODE)                                                                                          \
+    e = cudaFuncSetAttribute(k_rows2<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    if (e != cudaSuccess) return e;                                                                                    \
+    k_rows2<false, MODE><<<grid, 256, smem, st>>>(p)
+    switch (mode) {
+        case ROWS2_WRITE_REAL: ROWS2_WRITE_CASE(ROWS2_WRITE_REAL); break;
+        case ROWS2_WRITE_POWER: ROWS2_WRITE_CASE(ROWS2_WRITE_POWER); break;
+        case ROWS2_WRITE_REAL2: ROWS2_WRITE_CASE(ROWS2_WRITE_REAL2); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef ROWS2_WRITE_CASE
+    return cudaGetLastError();
+}
+
 template <int M1>
 static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);

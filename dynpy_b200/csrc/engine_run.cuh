@@ -4,11 +4,14 @@
 #include "fft_engine.cuh"
 #include "fft_rows2.cuh"
 #include "common.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace dynpy {
 
 // defined in dd2.cu
 cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int n_sm, cudaStream_t st);
+cudaError_t launch_rows2_write(Rows2Params p, int mode, int n_sm, cudaStream_t st);
 
 template <int L, bool TWO_PASS, class Loader, int MODE>
 static cudaError_t launch_rows_L(const Loader& ld, const EpiParams& ep, const cd* tw, i64 f0, i64 f1, int gy,
@@ -142,9 +145,21 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
             for (int s = 0; s < nslots; ++s) sel[s] = s;
             e = launch_rows2(rp, sel, nslots, false, n_sm, st);
         } else {
-            TLoader tl;
-            tl.T = T; tl.M1 = M1; tl.f_base = f0;
-            e = launch_rows_L<DYNPY_ROW_LEN, true, TLoader, MODE>(tl, ep, tw, f0, f1, ys * nslots, M1, st);
+            // write epilogues (per-series power spectra, inverse transforms): the same row kernel; for A/B,
+            // DYNPY_ROWS_GENERIC=1 keeps the plain radix kernel k_rows for all of them, =2 for the real-output modes only
+            static int generic = -1;
+            if (generic < 0) { const char* g = getenv("DYNPY_ROWS_GENERIC"); generic = g ? atoi(g) : 0; }
+            if (generic == 0 || (generic == 2 && MODE == EPI_WRITE_POWER)) {
+                Rows2Params rp;
+                memset(&rp, 0, sizeof(rp));
+                rp.T = T; rp.M = M; rp.M1 = M1; rp.rs = DYNPY_ROW_LEN; rp.items = nb; rp.twp = tw;
+                rp.out = ep.out; rp.f_base = f0; rp.n_out = ep.n_out; rp.n_series = ep.n_series; rp.scale = ep.scale;
+                e = launch_rows2_write(rp, MODE, n_sm, st);
+            } else {
+                TLoader tl;
+                tl.T = T; tl.M1 = M1; tl.f_base = f0;
+                e = launch_rows_L<DYNPY_ROW_LEN, true, TLoader, MODE>(tl, ep, tw, f0, f1, ys * nslots, M1, st);
+            }
         }
         if (e != cudaSuccess) return e;
     }

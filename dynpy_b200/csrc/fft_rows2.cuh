@@ -59,7 +59,15 @@ struct Rows2Params {
     int fix_slot;
     double inv_n;
     int pf_dist;            // rows of look-ahead of the L2 bulk prefetch (0: off)
+    // write modes (MODE != 0): T holds transforms f_base .. f_base + items - 1 (nslots = 1), units ordered (f, k1)
+    double* out;            // WRITE_POWER: P[f][M] internal order; WRITE_REAL(2): out[f (2f, 2f+1)][n_out], k = k1 + M1 k2
+    i64 f_base;
+    i64 n_out;
+    i64 n_series;           // WRITE_REAL2: second output row exists while 2 f + 1 < n_series
+    double scale;
 };
+// epilogues of the row kernel (the values of fft_engine.cuh's EpiMode)
+enum Rows2Mode { ROWS2_ACC_POWER = 0, ROWS2_WRITE_REAL = 1, ROWS2_WRITE_POWER = 2, ROWS2_WRITE_REAL2 = 3 };
 
 __device__ __forceinline__ cd ldcg_cd2(const cd* p) {
     double2 r;
@@ -67,13 +75,19 @@ __device__ __forceinline__ cd ldcg_cd2(const cd* p) {
     return r;
 }
 
-template <bool FIX>
+template <bool FIX, int MODE = ROWS2_ACC_POWER>
 __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     extern __shared__ double2 smem[];
     const int tid = threadIdx.x;
-    const i64 units = (i64)p.nsel * p.M1 * p.items;
-    const i64 u0 = units * blockIdx.x / gridDim.x;
-    const i64 u1 = units * (blockIdx.x + 1) / gridDim.x;
+    const i64 units = (MODE == ROWS2_ACC_POWER ? (i64)p.nsel : (i64)1) * p.M1 * p.items;
+    // accumulate / power modes: equal contiguous ranges; real-output modes: rows dealt round-robin (ustep = grid size), so
+    // that at any moment the CTAs of the grid hold CONSECUTIVE rows k1 of the same few transforms — their 8-byte
+    // outputs k = k1 + M1 k2 share 32-byte sectors, which are then completed in L2 within one row time (with
+    // contiguous ranges a sector's four writers were microseconds apart: 3.5 x the DRAM write traffic, read-fills)
+    constexpr bool RR = MODE == ROWS2_WRITE_REAL || MODE == ROWS2_WRITE_REAL2;
+    const i64 ustep = RR ? (i64)gridDim.x : 1;
+    const i64 u0 = RR ? (i64)blockIdx.x : units * blockIdx.x / gridDim.x;
+    const i64 u1 = RR ? units : units * (blockIdx.x + 1) / gridDim.x;
     if (u0 >= u1) return;
 
     const int h = tid >> 4, m = tid & 15;
@@ -98,19 +112,39 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     struct Cursor { int si, k1; i64 item; };
     auto decode = [&](i64 u) -> Cursor {
         Cursor c;
+        if constexpr (MODE != ROWS2_ACC_POWER) {   // (f, k1), k1 fastest: the rows of one transform stay together
+            c.si = 0;
+            c.item = u / p.M1;
+            c.k1 = (int)(u - c.item * p.M1);
+            return c;
+        }
         const i64 sk = u / p.items;
         c.item = u - sk * p.items;
         c.si = (int)(sk / p.M1);
         c.k1 = (int)(sk - (i64)c.si * p.M1);
         return c;
     };
+    const int rr_dk = (int)(ustep % p.M1);
+    const i64 rr_di = ustep / p.M1;
     auto advance = [&](Cursor& c) {
+        if constexpr (RR) {
+            c.k1 += rr_dk; c.item += rr_di;
+            if (c.k1 >= p.M1) { c.k1 -= p.M1; ++c.item; }
+            return;
+        }
+        if constexpr (MODE != ROWS2_ACC_POWER) {
+            if (++c.k1 == p.M1) { c.k1 = 0; ++c.item; }
+            return;
+        }
         if (++c.item == p.items) {
             c.item = 0;
             if (++c.k1 == p.M1) { c.k1 = 0; ++c.si; }
         }
     };
-    auto slot_of = [&](const Cursor& c) -> int { return (int)((p.sel_pack >> (4 * c.si)) & 15ull); };
+    auto slot_of = [&](const Cursor& c) -> int {
+        if constexpr (MODE != ROWS2_ACC_POWER) return 0;
+        return (int)((p.sel_pack >> (4 * c.si)) & 15ull);
+    };
     auto ptr_of = [&](const Cursor& c) -> const cd* {
         return p.T + ((T_ITEM(c.item) * p.nslots + slot_of(c)) * p.M1 + c.k1) * (i64)p.rs;
     };
@@ -130,7 +164,8 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     // element n2 = tid + 256 q of a row: tile (tid / TILE) + (256 / TILE) q, offset tid % TILE
     auto t_off = [&](int q) -> i64 { return tid + 256 * q; };
     Cursor cur = decode(u0);
-    Cursor pfc = decode(u0 + (p.pf_dist > 0 ? p.pf_dist : 0) < u1 ? u0 + (p.pf_dist > 0 ? p.pf_dist : 0) : u0);   // prefetch cursor
+    const i64 pf_ahead = (p.pf_dist > 0 ? p.pf_dist : 0) * ustep;
+    Cursor pfc = decode(u0 + pf_ahead < u1 ? u0 + pf_ahead : u0);   // prefetch cursor
     int slot = slot_of(cur), k1 = cur.k1;
     i64 item = cur.item;
     const cd* src = ptr_of(cur);
@@ -141,7 +176,7 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
     for (int q = 0; q < 16; ++q) nx[q] = ldcg_cd2(src + t_off(q));
 #endif
 
-    for (i64 u = u0; u < u1; ++u) {
+    for (i64 u = u0; u < u1; u += ustep) {
         cd v[16];
 #if DYNPY_ROWS_NX
 #pragma unroll
@@ -170,12 +205,12 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
         // L2 by one bulk prefetch per chunk (DRAM latency under this load is several microseconds)
         int nslot = slot, nk1 = k1;
         i64 nitem = item;
-        if (u + 1 < u1) {
+        if (u + ustep < u1) {
             advance(cur);
             src = ptr_of(cur);
             nslot = slot_of(cur); nk1 = cur.k1; nitem = cur.item;
         }
-        if (p.pf_dist > 0 && u + p.pf_dist < u1) {
+        if (p.pf_dist > 0 && u + pf_ahead < u1) {
             if (tid == 0) {
                 const cd* pf = ptr_of(pfc);
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(4096 * 16) : "memory");
@@ -208,9 +243,36 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
 #endif
         __syncthreads();  // every thread has its step-3 inputs: the buffer may be rewritten
         fft16(v);
+        if constexpr (MODE == ROWS2_ACC_POWER) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc[j]));
-        if (u + 1 == u1 || nslot != slot || nk1 != k1) flush(slot, k1);
+            for (int j = 0; j < 16; ++j) acc[j] = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc[j]));
+            if (u + ustep >= u1 || nslot != slot || nk1 != k1) flush(slot, k1);
+        } else if constexpr (MODE == ROWS2_WRITE_POWER) {
+            // |X|^2 of the row, k2 = h + 16 m + 256 j, staged through a second shared-memory region (padded: k + k / 16)
+            // so that the row leaves as 256-byte runs; the region is rewritten only after the next row's two barriers
+            double* sr = reinterpret_cast<double*>(smem + pad16(4096) + 256);
+            const int kk0 = h + 17 * m;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sr[kk0 + 272 * j] = fma(v[j].x, v[j].x, v[j].y * v[j].y);
+            __syncthreads();
+            double* dst = p.out + (p.f_base + item) * p.M + ((i64)k1 << 12);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[tid + 256 * i] = sr[tid + (tid >> 4) + 272 * i];
+        } else {
+            // natural index k = k1 + M1 k2 (the M1 rows of a transform are consecutive units of the same CTA: the 32-byte
+            // sectors they share are completed in L2 a few microseconds apart)
+            const i64 f = p.f_base + item;
+            const bool two = MODE == ROWS2_WRITE_REAL2 && 2 * f + 1 < p.n_series;
+            double* o0 = p.out + (MODE == ROWS2_WRITE_REAL2 ? 2 * f : f) * p.n_out;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const i64 k = (i64)k1 + (i64)p.M1 * (h + 16 * m + 256 * j);
+                if (k < p.n_out) {
+                    o0[k] = v[j].x * p.scale;
+                    if (two) o0[p.n_out + k] = v[j].y * p.scale;
+                }
+            }
+        }
         slot = nslot; k1 = nk1; item = nitem;
     }
 }
