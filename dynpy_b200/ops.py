@@ -7,6 +7,8 @@ contiguous, float64 / int64 / int32 as documented; there is no CPU path.
 from __future__ import annotations
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -75,6 +77,8 @@ def fft_length(n: int) -> int:
 
 def _fft_ws(M: int, n_fft: int, device, budget: int = 2 << 30):
     lib = _lib.load()
+    if os.environ.get("DYNPY_FFT_WS_MB"):      # A/B knob: batch size of the generic engine (T resident in L2 or not)
+        budget = int(float(os.environ["DYNPY_FFT_WS_MB"]) * (1 << 20))
     one = lib.dynpy_fft_workspace_bytes(M, 1)
     if one == 0:
         return None, 0
