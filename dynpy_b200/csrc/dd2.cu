@@ -229,6 +229,8 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     ColsTpcParams tp;
     memset(&tp, 0, sizeof(tp));
     { const char* e = getenv("DYNPY_TPC_SYNC"); tp.sync_units = e ? atoi(e) : 1; }
+    i64 tpc_sub = 96;
+    { const char* e = getenv("DYNPY_TPC_SUB"); if (e) tpc_sub = atoll(e); }
     tp.N = N; tp.M = M; tp.rsum = rsum; tp.inv_n = 1.0 / (double)N; tp.seeds = TWT;  // the seed table shares the twiddle-table region (never both in one call)
     GeomParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -279,10 +281,22 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
                     k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
             }
             DYNPY_CHECK(cudaGetLastError(), "dd geometry");
-            tp.items = cnt;
-            tp.pair0 = 2 * it0;
+            // The column kernel deals its units round-robin; over the ~500 rounds of a 32 GiB batch its CTAs drift apart
+            // and the 11 series of an (item, column block) meet their geometry in L2 less often (ncu, 820 items per
+            // launch: 17.7 MB of geometry re-read from DRAM per item against 7.6 MB at 93 items, ideal 6.4).  The
+            // columns of a batch therefore go out in launches of `sub` items (DYNPY_TPC_SUB, 0 = the whole batch) while
+            // geometry and rows keep the whole batch: column pass 37.15 -> 36.5 ms per 8192 pairs (sub = 96 or 192).
             tp.n_pairs = P;
-            DYNPY_CHECK(launch_cols_tpc(tp, tw, n_sm, st), "dd columns");
+            const bool single = (M >> 12) > 64;   // the long-column kernels walk tiles, not units: one launch
+            const i64 sub = (single || tpc_sub <= 0) ? cnt : tpc_sub;
+            for (i64 s0 = 0; s0 < cnt; s0 += sub) {
+                tp.items = cnt - s0 < sub ? cnt - s0 : sub;
+                tp.pair0 = 2 * (it0 + s0);
+                tp.Gs = Gs + s0 * 4 * N;
+                tp.T = T + s0 * (i64)DD_NSLOTS * (t_bytes(M) / (i64)sizeof(cd));
+                tp.rsum = rsum + 2 * s0;
+                DYNPY_CHECK(launch_cols_tpc(tp, tw, n_sm, st), "dd columns");
+            }
         } else {
             cp.pair0 = 2 * it0;
             cp.items = cnt;
