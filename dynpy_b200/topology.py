@@ -237,15 +237,30 @@ class _LazyPairs(dict):
 
     def __init__(self, ev: np.ndarray):
         super().__init__()
-        frames, first = np.unique(ev[:, 0], return_index=True) if len(ev) else (np.empty(0, np.int64), np.empty(0, np.int64))
         self._ev = ev
-        self._span = dict(zip(frames.tolist(), zip(first.tolist(), np.append(first[1:], len(ev)).tolist())))
+        if len(ev):   # rows are sorted by frame: group boundaries in one pass, no sort
+            f = ev[:, 0]
+            self._first = np.flatnonzero(np.concatenate([[True], f[1:] != f[:-1]]))
+            self._fr = f[self._first]
+        else:
+            self._first = np.empty(0, np.int64)
+            self._fr = np.empty(0, np.int64)
+        self._span_ = None
+
+    @property
+    def _span(self):
+        """{frame: (begin, end)} — a python dict over ~1e5 frames costs ~15 ms, so it is only built when a caller
+        looks frames up or iterates (len() and bool() do not need it)"""
+        if self._span_ is None:
+            last = np.append(self._first[1:], len(self._ev))
+            self._span_ = dict(zip(self._fr.tolist(), zip(self._first.tolist(), last.tolist())))
+        return self._span_
 
     def __len__(self):
-        return len(self._span)
+        return int(len(self._fr))
 
     def __bool__(self):
-        return bool(self._span)
+        return len(self._fr) > 0
 
     def __contains__(self, f):
         return f in self._span

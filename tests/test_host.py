@@ -395,3 +395,20 @@ def test_derived_topology_equals_full_reindexing():
         np.testing.assert_array_equal(der.classify_exact({"O": 1, "H": 2}) if any(
             full.formula(m) == {"O": 1, "H": 2} for m in range(full.nmol)) else [], full.classify_exact(
             {"O": 1, "H": 2}) if any(full.formula(m) == {"O": 1, "H": 2} for m in range(full.nmol)) else [])
+
+
+def test_deviating_frame_lists_group_lazily():
+    """{frame: [(i, j)]} view over the device scan's sorted event rows (topology._LazyPairs): sizes and truth value
+    without building per-frame lists, look-ups and iteration in frame order, empty scan."""
+    from dynpy_b200 import topology
+    ev = np.array([[2, 1, 5], [2, 3, 4], [7, 0, 1], [9, 2, 3], [9, 2, 4], [9, 5, 6]], dtype=np.int64)
+    lp = topology._group_events(ev)
+    assert len(lp) == 3 and bool(lp) and 7 in lp and 3 not in lp
+    assert lp[2] == [(1, 5), (3, 4)] and lp[9] == [(2, 3), (2, 4), (5, 6)]
+    assert list(lp.keys()) == [2, 7, 9] and list(lp) == [2, 7, 9]
+    assert dict(lp.items()) == {2: [(1, 5), (3, 4)], 7: [(0, 1)], 9: [(2, 3), (2, 4), (5, 6)]}
+    # rows that arrive unsorted (merged per-rank lists) are sorted by (frame, i, j) first
+    lp2 = topology._group_events(ev[[3, 0, 5, 2, 1, 4]])
+    assert dict(lp2.items()) == dict(lp.items())
+    empty = topology._group_events(np.empty((0, 3), np.int64))
+    assert len(empty) == 0 and not empty and list(empty.items()) == []

@@ -1,0 +1,5 @@
+#!/bin/bash
+out=gpurun_out/r2f; mkdir -p $out
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512"
+timeout 300 $T bench.py --gpus 8 --steps 3 --warmup 3 > $out/bench_cfg2_8gpu.json 2> $out/bench_cfg2_8gpu.err; echo "cfg2 rc=$?"; tail -c 400 $out/bench_cfg2_8gpu.err; cut -c1-260 $out/bench_cfg2_8gpu.json
+timeout 300 $T bench.py --gpus 8 --workload cfg3 --steps 5 --warmup 3 > $out/bench_cfg3_8gpu.json 2> $out/bench_cfg3_8gpu.err; echo "cfg3 rc=$?"; tail -c 400 $out/bench_cfg3_8gpu.err; cut -c1-260 $out/bench_cfg3_8gpu.json
