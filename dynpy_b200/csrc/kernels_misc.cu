@@ -255,15 +255,14 @@ cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const in
 // out[1] = first frame with a mismatch, out[2] = number of events listed.
 //
 // O(A^2 F) pair-frames, but almost all of them are far apart: a thread owns one frame and a tile of
-// TOPO_TI atoms i whose x coordinates stay in registers; for every j it loads x_j once (a coalesced 1 KB run
-// per warp... consecutive threads = consecutive frames) and screens the TI pairs with three fp64 instructions
-// each — nearest-image |dx| against T = the largest bond threshold; y and z are loaded and screened only for
-// the pairs that pass (lanes of a warp are consecutive frames of the SAME pair, so the branches are nearly
-// uniform).  Only pairs inside the T-cube (a fraction (2T/L)^3) take the exact path: the bit-exact per-axis
-// minimum image of the pair kernels and the reference's comparison.  The expected bonds of the tile's atoms are
-// listed in shared memory once per CTA and verified in every frame first, so the screened sweep only has to
-// find bonds that are NOT expected.  Coordinates are swept A / TOPO_TI times through L2 (the CTAs of one
-// frame chunk are adjacent in the grid) instead of A / 2 times.
+// TOPO_TI atoms i whose coordinates stay in (float) registers; for every j it loads x_j, y_j, z_j once (coalesced
+// 1 KB runs per warp: consecutive threads = consecutive frames) and screens the TI pairs on all three axes —
+// nearest-image |d| against T = the largest bond threshold, with a margin that keeps the fp32 screen a superset.
+// Only pairs inside the T-cube (a fraction (2T/L)^3) take the exact path: the bit-exact per-axis minimum image of
+// the pair kernels and the reference's comparison (lanes of a warp are consecutive frames of the SAME pair, so the
+// branch is nearly uniform).  The expected bonds of the tile's atoms are listed in shared memory once per CTA and
+// verified in every frame first, so the screened sweep only has to find bonds that are NOT expected.  Coordinates
+// are swept A / TOPO_TI times through L2 (the CTAs of one frame chunk are adjacent in the grid) instead of A / 2 times.
 #define TOPO_TI 8
 #define TOPO_NT 128
 #define TOPO_BCAP 128
@@ -276,12 +275,8 @@ __device__ __forceinline__ bool topo_bond_exact(const double* __restrict__ X, i6
     const double r2 = __dadd_rn(__dadd_rn(sx, sy), sz);
     return (r2 < dmax2) && (sqrt(r2) <= __dadd_rn(__dadd_rn(ri, rj), extra));
 }
-// Is the nearest of the images -1, 0, +1 along one axis possibly within T?  min(|d|, ||d| - a|) <= T  is implied
-// by  ||d| - a/2| >= a/2 - T  (equivalent for |d| <= a, a superset beyond): three fp64 instructions, no fmin
-// (which costs a DSETP + two selects + NaN fix-up here).  h = a / 2, thr = a / 2 - T.
-__device__ __forceinline__ bool topo_axis_near(double xi, double xj, double h, double thr) {
-    return fabs(fabs(xi - xj) - h) >= thr;
-}
+// Screen of one axis: is the nearest of the images -1, 0, +1 possibly within T?  min(|d|, ||d| - a|) <= T  is implied
+// by  ||d| - a/2| >= a/2 - T  (equivalent for |d| <= a, a superset beyond): three instructions per axis, no fmin.
 __global__ void __launch_bounds__(TOPO_NT)
 k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __restrict__ rcov, double extra,
                  const unsigned char* __restrict__ expect, double a, double b, double c, double dmax2,
@@ -345,30 +340,41 @@ k_topology_check(const double* __restrict__ X, i64 A, i64 N, const double* __res
                     !topo_bond_exact(X, N, n, i0 + k, j, rcov[i0 + k], rcov[j], extra, a, b, c, dmax2))
                     report(i0 + k, j);
     }
-    // ---- screened sweep: bonds that are not expected
-    double xi[TOPO_TI];
+    // ---- screened sweep: bonds that are not expected.  All three axes are screened at once, in fp32: the tile's
+    // coordinates sit in 24 float registers, x_j / y_j / z_j are loaded (coalesced over frames) and converted once per
+    // j, and a pair costs nine full-rate fp32 instructions; the thresholds are widened by far more than the rounding
+    // of the conversions and differences (1e-5 of the box edge against ~2e-7), so the screen stays a superset and
+    // every pair that passes (a fraction (2T/L)^3 ~ 0.6 % at cfg2) takes the exact fp64 path.  Screening x alone in
+    // fp64 sent 80 % of the j iterations of an 8-atom tile into the slow branch: 59 ms per 768 atoms x 1e5 frames.
+    float xi[TOPO_TI], yi[TOPO_TI], zi[TOPO_TI];
 #pragma unroll
-    for (int k = 0; k < TOPO_TI; ++k) xi[k] = k < ti ? X[((i0 + k) * 3 + 0) * N + n] : 0.0;
+    for (int k = 0; k < TOPO_TI; ++k) {
+        xi[k] = k < ti ? (float)X[((i0 + k) * 3 + 0) * N + n] : 0.0f;
+        yi[k] = k < ti ? (float)X[((i0 + k) * 3 + 1) * N + n] : 0.0f;
+        zi[k] = k < ti ? (float)X[((i0 + k) * 3 + 2) * N + n] : 0.0f;
+    }
+    const float haf = (float)ha, hbf = (float)hb, hcf = (float)hc;
+    const float taf = (float)ta - (float)(1e-5 * a + 1e-6), tbf = (float)tb - (float)(1e-5 * b + 1e-6),
+                tcf = (float)tc - (float)(1e-5 * c + 1e-6);
     for (i64 j = i0 + 1; j < A; ++j) {
-        const double xj = __ldg(X + (j * 3 + 0) * N + n);
+        const float xj = (float)__ldg(X + (j * 3 + 0) * N + n);
+        const float yj = (float)__ldg(X + (j * 3 + 1) * N + n);
+        const float zj = (float)__ldg(X + (j * 3 + 2) * N + n);
         unsigned near = 0;
 #pragma unroll
-        for (int k = 0; k < TOPO_TI; ++k)
-            if (topo_axis_near(xi[k], xj, ha, ta)) near |= 1u << k;
+        for (int k = 0; k < TOPO_TI; ++k) {
+            const bool nr = fabsf(fabsf(xi[k] - xj) - haf) >= taf && fabsf(fabsf(yi[k] - yj) - hbf) >= tbf &&
+                            fabsf(fabsf(zi[k] - zj) - hcf) >= tcf;
+            near |= nr ? (1u << k) : 0u;
+        }
         if (j - i0 < TOPO_TI) near &= (1u << (j - i0)) - 1u;   // pairs with i0 + k < j only
         near &= (1u << ti) - 1u;
-        if (near) {
-            const double yj = __ldg(X + (j * 3 + 1) * N + n);
-            const double zj = __ldg(X + (j * 3 + 2) * N + n);
-            while (near) {
-                const int k = __ffs(near) - 1;
-                near &= near - 1;
-                const i64 i = i0 + k;
-                if (!topo_axis_near(X[(i * 3 + 1) * N + n], yj, hb, tb)) continue;
-                if (!topo_axis_near(X[(i * 3 + 2) * N + n], zj, hc, tc)) continue;
-                if (topo_bond_exact(X, N, n, i, j, rcov[i], rcov[j], extra, a, b, c, dmax2) && !expect[i * A + j])
-                    report(i, j);
-            }
+        while (near) {
+            const int k = __ffs(near) - 1;
+            near &= near - 1;
+            const i64 i = i0 + k;
+            if (topo_bond_exact(X, N, n, i, j, rcov[i], rcov[j], extra, a, b, c, dmax2) && !expect[i * A + j])
+                report(i, j);
         }
     }
     if (bad) {
