@@ -749,36 +749,62 @@ __global__ void __launch_bounds__(Tpc3Shape<B, C>::NT, PER_SM) k_cols_tpc3(const
         // series in three groups that share their two streams: complex series of p (streams 0, 1), of q (2, 3),
         // packed real series of p + i q (1, 3)
         cd GA[GS ? 1 : 8], GB[GS ? 1 : 8];
-        auto ga = [&](int a) -> cd { if constexpr (GS) return ZG[a * Shape::NT]; else return GA[a]; };
-        auto gb = [&](int a) -> cd { if constexpr (GS) return ZG[(8 + a) * Shape::NT]; else return GB[a]; };
+        // GS: the zone holds two streams in halves 0 and 1.  Group order  p complex (x,y | z,r3 of p) -> packed real
+        // (z,r3 of p | z,r3 of q) -> q complex (x,y | z,r3 of q): every change of group replaces ONE stream, and that
+        // copy is issued as soon as the last series of the old group has formed its samples, so it lands under that
+        // series' phase C instead of being waited for (the copies were 11 % of the kernel's stall samples).
+        //   half 0: (x,y)_p  -> (z,r3)_q            half 1: (z,r3)_p  -> (x,y)_q   (idx >= 7)
+        // roles: idx 0-3  ga = half 0, gb = half 1 | idx 4-6  ga = half 1, gb = half 0 | idx 7-10  ga = half 1, gb = half 0
+        // (the roles are compile-time: every kind of series is instantiated for the placement its group uses)
+        auto gz = [&](int half, int a) -> cd { return ZG[(8 * half + a) * Shape::NT]; };
+        auto copy_stream = [&](const cd* src, int half) {   // 8 copies of this thread's residue into one half of its zone
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
+                cp_async16_zfill(ZG + (8 * half + a) * Shape::NT, src + fr, (onmask >> a) & 1u);
+            }
+        };
+        if constexpr (GS) {
+            if (item == (i64)blockIdx.y) {   // first item of this CTA: nothing was prefetched
+                copy_stream(g, 0);
+                copy_stream(g + N, 1);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
 #pragma unroll 1
         for (int idx = 0; idx < 11; ++idx) {
-            const int slot = idx < 8 ? ((idx & 3) == 0 ? 1 : (idx & 3) == 1 ? 3 : (idx & 3) == 2 ? 7 : 9) + (idx >> 2)
-                                     : (idx == 8 ? 0 : idx - 4);
-            if (idx == 0 || idx == 4 || idx == 8) {
-                const cd* sa = g + (idx == 0 ? 0 : idx == 4 ? 2 : 1) * N;
-                const cd* sb = g + (idx == 0 ? 1 : 3) * N;
+            int slot;
+            if constexpr (GS) {
+                // idx 0-3: Y21, Y22, F21, F22 of p | 4-6: Y20, r^-3, F20 (packed) | 7-10: Y21, Y22, F21, F22 of q
+                slot = idx < 4 ? (idx == 0 ? 1 : idx == 1 ? 3 : idx == 2 ? 7 : 9)
+                     : idx < 7 ? (idx == 4 ? 0 : idx + 0)
+                               : (idx == 7 ? 2 : idx == 8 ? 4 : idx == 9 ? 8 : 10);
+                if (idx == 0 || idx == 4 || idx == 7) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else {
+                slot = idx < 8 ? ((idx & 3) == 0 ? 1 : (idx & 3) == 1 ? 3 : (idx & 3) == 2 ? 7 : 9) + (idx >> 2)
+                               : (idx == 8 ? 0 : idx - 4);
+                if (idx == 0 || idx == 4 || idx == 8) {
+                    const cd* sa = g + (idx == 0 ? 0 : idx == 4 ? 2 : 1) * N;
+                    const cd* sb = g + (idx == 0 ? 1 : 3) * N;
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
-                    const bool on = (onmask >> a) & 1u;
-                    const cd zero = make_double2(0.0, 0.0);
-                    if constexpr (GS) {
-                        cp_async16_zfill(ZG + a * Shape::NT, sa + fr, on);
-                        cp_async16_zfill(ZG + (8 + a) * Shape::NT, sb + fr, on);
-                    } else {
+                    for (int a = 0; a < 8; ++a) {
+                        const i64 fr = (i64)(B * a + bA) * 4096 + n2A;
+                        const bool on = (onmask >> a) & 1u;
+                        const cd zero = make_double2(0.0, 0.0);
                         GA[a] = on ? ldg_cd(sa + fr) : zero;
                         GB[a] = on ? ldg_cd(sb + fr) : zero;
                     }
                 }
-                if constexpr (GS) asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             }
             // ---- phase A: the 8 samples of residue b, one specialised block per kind of series (the slot is uniform
             // over the CTA).  Frames beyond the series and a missing second pair arrive as zero geometry, which makes
             // every series with a factor x, y, z or r^-3 vanish; only Y20 and r^-3 - <r^-3> switch their constant off.
             cd v[8];
-            auto form = [&](auto kind) {
+            auto form = [&](auto kind, auto swapped) {
                 constexpr int K = decltype(kind)::value;   // 0 Y20 | 5 r^-3 | 6 F20 | 1 Y21 | 3 Y22 | 7 F21 | 9 F22
+                constexpr bool SW = decltype(swapped)::value;   // GS: first stream of the group in half 1, second in half 0
+                auto ga = [&](int a) -> cd { if constexpr (GS) return gz(SW ? 1 : 0, a); else return GA[a]; };
+                auto gb = [&](int a) -> cd { if constexpr (GS) return gz(SW ? 0 : 1, a); else return GB[a]; };
                 if constexpr (K == 0 || K == 5 || K == 6) {   // GA, GB = (z/r, r^-3) of p, q -> re + i im
                     const unsigned onq = q_exists ? onmask : 0u;
 #pragma unroll
@@ -809,14 +835,32 @@ __global__ void __launch_bounds__(Tpc3Shape<B, C>::NT, PER_SM) k_cols_tpc3(const
                     }
                 }
             };
-            switch (slot) {
-                case 0: form(TpcKind<0>{}); break;
-                case 5: form(TpcKind<5>{}); break;
-                case 6: form(TpcKind<6>{}); break;
-                case 1: case 2: form(TpcKind<1>{}); break;
-                case 3: case 4: form(TpcKind<3>{}); break;
-                case 7: case 8: form(TpcKind<7>{}); break;
-                default: form(TpcKind<9>{}); break;
+            using SwNo = std::integral_constant<bool, false>;
+            using SwYes = std::integral_constant<bool, true>;
+            if constexpr (GS) {   // p complex: (x,y) in half 0, (z,r3) in half 1; packed and q complex: the other way round
+                switch (slot) {
+                    case 0: form(TpcKind<0>{}, SwYes{}); break;
+                    case 5: form(TpcKind<5>{}, SwYes{}); break;
+                    case 6: form(TpcKind<6>{}, SwYes{}); break;
+                    case 1: form(TpcKind<1>{}, SwNo{}); break;
+                    case 2: form(TpcKind<1>{}, SwYes{}); break;
+                    case 3: form(TpcKind<3>{}, SwNo{}); break;
+                    case 4: form(TpcKind<3>{}, SwYes{}); break;
+                    case 7: form(TpcKind<7>{}, SwNo{}); break;
+                    case 8: form(TpcKind<7>{}, SwYes{}); break;
+                    case 9: form(TpcKind<9>{}, SwNo{}); break;
+                    default: form(TpcKind<9>{}, SwYes{}); break;
+                }
+            } else {
+                switch (slot) {
+                    case 0: form(TpcKind<0>{}, SwNo{}); break;
+                    case 5: form(TpcKind<5>{}, SwNo{}); break;
+                    case 6: form(TpcKind<6>{}, SwNo{}); break;
+                    case 1: case 2: form(TpcKind<1>{}, SwNo{}); break;
+                    case 3: case 4: form(TpcKind<3>{}, SwNo{}); break;
+                    case 7: case 8: form(TpcKind<7>{}, SwNo{}); break;
+                    default: form(TpcKind<9>{}, SwNo{}); break;
+                }
             }
             if constexpr (!Shape::SPLIT_A) {
                 cd e[8];
@@ -840,6 +884,17 @@ __global__ void __launch_bounds__(Tpc3Shape<B, C>::NT, PER_SM) k_cols_tpc3(const
                 for (int c = 1; c < 16; c += 2) smem[c * SROW + bA * C + colA] = cmul(v[c >> 1], TA[c * B + bA]);
             }
             __syncthreads();
+            if constexpr (GS) {   // phase A is done, no sample registers are live: the stream the next group replaces may be
+                                  // overwritten now; the copy lands under phase C
+                if (idx == 3) { copy_stream(g + 3 * N, 0); asm volatile("cp.async.commit_group;" ::: "memory"); }
+                if (idx == 6) { copy_stream(g + 2 * N, 1); asm volatile("cp.async.commit_group;" ::: "memory"); }
+                if (idx == 10 && item + gridDim.y < p.items) {
+                    const cd* gn = p.Gs + (item + gridDim.y) * 4 * N;
+                    copy_stream(gn, 0);
+                    copy_stream(gn + N, 1);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            }
             // ---- phase C: B-point transform over b for (c, column)
             cd u[HB];
             if constexpr (Shape::SPLIT_C) {   // parity `par`: sums / differences of the two halves, B/2-point codelet
