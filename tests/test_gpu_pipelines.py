@@ -153,11 +153,11 @@ def test_dd_kernels_vs_oracle_bigger(ops):
             assert info["partial"] > 0 and info["full"] > 0
 
 
-def test_dd_pair_count_bit_exact_presence(ops):
+@pytest.mark.parametrize("F", [64, 62, 1028])   # 32-byte loads (F % 4 == 0, more than one sweep of 1024 frames) and the scalar form
+def test_dd_pair_count_bit_exact_presence(ops, F):
     """Presence (r2 < rmax^2) must agree with pdist_ortho's decision for every pair-frame."""
     from dynpy_b200 import synth
     box = synth.water_box(8, seed=5)
-    F = 64
     traj = box.frames(0, F)
     L = box.celldm
     w = np.mod(traj.numpy(), L)
