@@ -167,7 +167,7 @@ template <int M1>
 static cudaError_t launch_cols_tpc_M1(const ColsTpcParams& p, int n_sm, cudaStream_t st) {
     ProfScope prof(PROF_COLS, st);
     constexpr int TPC_THREADS = TpcShape<M1>::NT;
-    const size_t smem = (size_t)(M1 / 2) * TPC_THREADS * sizeof(cd);  // per-thread landing zone / sample stash
+    const size_t smem = (size_t)((TPC_DUAL && M1 < 64) ? M1 : M1 / 2) * TPC_THREADS * sizeof(cd);  // per-thread landing zone / sample stash
     cudaError_t e = cudaFuncSetAttribute(k_cols_tpc<M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = TpcShape<M1>::PER_SM;

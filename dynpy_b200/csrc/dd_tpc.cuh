@@ -340,6 +340,11 @@ __device__ __forceinline__ void st_stream(cd* p, cd v) {
 #ifndef TPC_PER_SM
 #define TPC_PER_SM (512 / TPC_NT)
 #endif
+// 1 (A/B, with TPC_NT = 128 and TPC_PER_SM = 2): the zone holds BOTH streams of a series (2 H entries per thread), the
+// second stream of the next series is copied under the even half, the first under the odd half: no copy is waited for
+#ifndef TPC_DUAL
+#define TPC_DUAL 0
+#endif
 #ifndef TPC64_PER_SM
 #define TPC64_PER_SM 2   // M1 = 64: 32-point halves need ~250 registers; 2 x 128 threads without spills beat 3 x 128 with
 #endif
@@ -433,6 +438,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
     constexpr int TPC_THREADS = TpcShape<M1>::NT;
     constexpr int NCB = (4096 + TPC_THREADS - 1) / TPC_THREADS;  // the last column block may be partial
     constexpr bool RAGGED = (4096 % TPC_THREADS) != 0;
+    constexpr bool DUAL = TPC_DUAL != 0 && M1 < 64;
     extern __shared__ double2 smem[];
     // thread-private zone of H double2 at zone[j * TPC_THREADS]: landing area of the two geometry streams (one
     // cp.async burst each: all H loads of a stream are in flight together, L2 latency is paid twice per
@@ -461,13 +467,17 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
             const int jlim = (nfr > n2 && (!RAGGED || n2 < 4096)) ? (nfr - n2 + 4095) >> 12 : 0;
             // rows j >= jlim are zero-filled (src-size 0: nothing is read; the address still lies inside the
             // workspace, whose T region follows the geometry streams)
-            cp_async_burst<TPC_THREADS * 16, 4096 * 16>((unsigned)__cvta_generic_to_shared(zone), src, jlim,
-                                                         std::make_integer_sequence<int, H>{});
+            cd* dstz = (DUAL && which) ? zone + H * TPC_THREADS : zone;
+            if (!(DUAL && which && (slot == 3 || slot == 4)))   // Y22 has no second stream
+                cp_async_burst<TPC_THREADS * 16, 4096 * 16>((unsigned)__cvta_generic_to_shared(dstz), src, jlim,
+                                                             std::make_integer_sequence<int, H>{});
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const cd* zoneB = DUAL ? zone + H * TPC_THREADS : zone;   // where the second stream of a series is read
 
     issue_stream(blockIdx.x, 0);
+    if (DUAL) issue_stream(blockIdx.x, 1);
     for (i64 u = blockIdx.x; u < units; u += gridDim.x) {
         const int slot = (int)(u % nslots);
         const i64 ic = u / nslots;
@@ -500,10 +510,12 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
                 };
 #pragma unroll
                 for (int j = 0; j < H; ++j) v[j].x = real_word(zone[j * TPC_THREADS], j, jlim, mean_p);
-                issue_stream(u, 1);
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (!DUAL) {
+                    issue_stream(u, 1);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
 #pragma unroll
-                for (int j = 0; j < H; ++j) v[j].y = real_word(zone[j * TPC_THREADS], j, jlim_q, mean_q);
+                for (int j = 0; j < H; ++j) v[j].y = real_word(zoneB[j * TPC_THREADS], j, jlim_q, mean_q);
             } else {
                 constexpr bool order1 = K == 1 || K == 7;
                 constexpr bool weighted = K >= 7;
@@ -521,11 +533,13 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
                         const cd xy = zone[j * TPC_THREADS];
                         v[j] = order1 ? xy : make_double2(xy.x * xy.x - xy.y * xy.y, 2.0 * xy.x * xy.y);
                     }
-                    issue_stream(u, 1);
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    if (!DUAL) {
+                        issue_stream(u, 1);
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
 #pragma unroll
                     for (int j = 0; j < H; ++j) {
-                        const cd zr = zone[j * TPC_THREADS];
+                        const cd zr = zoneB[j * TPC_THREADS];
                         const double sc = c * (weighted ? zr.y : 1.0) * (order1 ? zr.x : 1.0);
                         v[j] = make_double2(sc * v[j].x, sc * v[j].y);
                     }
@@ -543,6 +557,7 @@ __global__ void __launch_bounds__(TpcShape<M1>::NT, TpcShape<M1>::PER_SM) k_cols
         }
 #pragma unroll
         for (int j = 0; j < H; ++j) zone[j * TPC_THREADS] = v[j];
+        if (DUAL) issue_stream(u + gridDim.x, 1);   // the second half of the zone is free: next series' second stream
         // even outputs
         ColCodelets<H>::even(v);
         tpc_store_chain<H, 0, 0>(dst, v, w2, w2, live);
