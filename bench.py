@@ -558,10 +558,13 @@ def native_arm(args, wl):
     # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture
     # (profiles/traffic.json holds bytes per pair-frame; one launch = one batch of the workspace)
     traffic = None
+    dram_per_pf = None
     launches = max(1.0, prof_n[dom] / args.steps)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh)[names[dom]]["bytes_per_pair_frame"] * pf_rank / launches
+            tj = json.load(fh)
+        traffic = tj[names[dom]]["bytes_per_pair_frame"] * pf_rank / launches
+        dram_per_pf = tj.get("whole_step_bytes_per_pair_frame")
     except Exception:
         pass
     alg_per_launch = ALG_BYTES_PER_PAIR_FRAME * pf_rank / launches
@@ -584,11 +587,12 @@ def native_arm(args, wl):
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "traffic": traffic, "algorithmic_bytes_per_launch": alg_per_launch,
                      "launch_ms": t_dom * 1e3 / launches, "peak_source": how,
-                     "ceilings": {"note": "measured on this pool (profiles/r01_ubench_ceilings.txt): the path is bound by fp64 issue "
-                                          "+ shared-memory/L1 wavefronts and by the T intermediate (2 x 16 B per transform point), "
-                                          "not by the 48 algorithmic bytes",
+                     "ceilings": {"note": "measured on this pool (profiles/r01_ubench_ceilings.txt): the path is bound by the fp64 pipe "
+                                          "(row kernel 62 % busy) and the L1 / shared-memory data pipe (column kernel ~70 %), "
+                                          "not by its 48 algorithmic bytes; the T intermediate (2 x 16 B per transform point) "
+                                          "makes the DRAM traffic ~9 x the algorithmic bytes",
                                   "hbm_copy_gbs": 6200.0, "l2_copy_gbs": 12400.0, "fp64_lanes_per_clk_per_sm": 63.5,
-                                  "dram_bytes_per_pair_frame": 488.0},
+                                  "dram_bytes_per_pair_frame": dram_per_pf},
                      "algorithmic_bytes_per_pair_frame": ALG_BYTES_PER_PAIR_FRAME,
                      "kernel_share_of_step": prof_ms[dom] / args.steps / ms_step,
                      "whole_step_frac": ALG_BYTES_PER_PAIR_FRAME * pf_rank / (ms_step * 1e-3) / 1e9 / hbm,
