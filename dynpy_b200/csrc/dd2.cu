@@ -82,6 +82,10 @@ static cudaError_t launch_cols_tpc2(const ColsTpcParams& p, const cd* tw, int n_
     return cudaGetLastError();
 }
 
+static inline dim3 geom_grid(i64 chunks, i64 slots, int pair_fastest) {
+    return pair_fastest ? dim3((unsigned)slots, (unsigned)chunks) : dim3((unsigned)chunks, (unsigned)slots);
+}
+
 template <int M1>
 static cudaError_t launch_cols_dd2_M1(const ColsDD2Params& p, int n_sm, cudaStream_t st) {
     auto kern = k_cols_dd2<M1>;
@@ -235,6 +239,7 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
     GeomParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.X = X; gp.pi = pi; gp.pj = pj; gp.n_pairs = P; gp.N = N; gp.a = a; gp.b = b; gp.c = c; gp.Gs = Gs; gp.rsum = rsum;
+    { const char* e = getenv("DYNPY_GEOM_ORDER"); gp.pair_fastest = (e && e[0] == 'f') ? 0 : 1; }   // "frames": A/B
     // column transform of the all-ones series (for the mean removal of G_r)
     if (tpc) {
         // the thread-per-column kernel removes the mean of r^-3 in the time domain (the sums are complete
@@ -276,9 +281,9 @@ int dd2_run(const double* X, i64 N, const int* pi, const int* pj, i64 P, double 
                                 "dd geometry (tma) attribute");
                     k_dd_geom_tma<<<2 * n_sm, GEOM_NT, smem, st>>>(gp);
                 } else if (vec && (N & 3) == 0 && ((uintptr_t)X & 31) == 0)
-                    k_dd_geom4<<<dim3((unsigned)((N + 2047) / 2048), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
+                    k_dd_geom4<<<geom_grid((N + 2047) / 2048, 2 * cnt, gp.pair_fastest), 256, 0, st>>>(gp);
                 else
-                    k_dd_geom<<<dim3((unsigned)((N + 1023) / 1024), (unsigned)(2 * cnt)), 256, 0, st>>>(gp);
+                    k_dd_geom<<<geom_grid((N + 1023) / 1024, 2 * cnt, gp.pair_fastest), 256, 0, st>>>(gp);
             }
             DYNPY_CHECK(cudaGetLastError(), "dd geometry");
             // The column kernel deals its units round-robin; over the ~500 rounds of a 32 GiB batch its CTAs drift apart

@@ -40,12 +40,16 @@ struct GeomParams {
     double a, b, c;
     cd* Gs;            // [n_slots][2][N] double2 streams: (x/r, y/r) and (z/r, r^-3)
     double* rsum;      // [n_slots] sums of r^-3 (zeroed by the caller)
+    int pair_fastest;  // 1: grid = (pair slots, frame chunks) — all pairs of the batch sweep one chunk of frames before the
+                       // next, so the coordinates of that chunk (A x 3 x 2048 frames) are read from DRAM once per batch
+                       // and then from L2; 0: grid = (frame chunks, pair slots), every pair streams its atoms from DRAM
 };
 
 // grid: (frame chunks of 1024, pair slots); 256 threads x 4 frames
 __global__ void __launch_bounds__(256) k_dd_geom(const GeomParams p) {
     __shared__ double sred[8];
-    const i64 slot = blockIdx.y;
+    const i64 slot = p.pair_fastest ? blockIdx.x : blockIdx.y;
+    const i64 chunk = p.pair_fastest ? blockIdx.y : blockIdx.x;
     const i64 pr = p.pair0 + slot;
     const bool exists = pr < p.n_pairs;
     const double* xi = p.X;
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(256) k_dd_geom(const GeomParams p) {
     double rs = 0.0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const i64 f = (i64)blockIdx.x * 1024 + e * 256 + threadIdx.x;
+        const i64 f = chunk * 1024 + e * 256 + threadIdx.x;
         if (f < p.N) {
             double gx = 0.0, gy = 0.0, gz = 0.0, g3 = 0.0;
             if (exists) {
@@ -106,7 +110,8 @@ __device__ __forceinline__ void stg256(cd* p, cd a, cd b) {
 // grid: (frame chunks of 2048, pair slots); 256 threads x 2 x 4 frames
 __global__ void __launch_bounds__(256) k_dd_geom4(const GeomParams p) {
     __shared__ double sred[8];
-    const i64 slot = blockIdx.y;
+    const i64 slot = p.pair_fastest ? blockIdx.x : blockIdx.y;
+    const i64 chunk = p.pair_fastest ? blockIdx.y : blockIdx.x;
     const i64 pr = p.pair0 + slot;
     const bool exists = pr < p.n_pairs;
     const double* xi = p.X;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) k_dd_geom4(const GeomParams p) {
     i64 f0[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        f0[e] = (i64)blockIdx.x * 2048 + e * 1024 + threadIdx.x * 4;
+        f0[e] = chunk * 2048 + e * 1024 + threadIdx.x * 4;
         if (f0[e] < p.N && exists) {
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
