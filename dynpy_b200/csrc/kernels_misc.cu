@@ -248,16 +248,23 @@ __device__ __forceinline__ void ldg256_nc(const double* p, double (&v)[4]) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
+// grid = (pairs, chunks of PC_CHUNK frames), pairs fastest: all pairs sweep one chunk of frames while its coordinates
+// (A x 3 x 4096 frames = 50 MB at 512 atoms) are in L2 — one CTA per pair streaming the whole trajectory re-read the
+// second atom of every pair from DRAM (130 816 pairs x 2.4 MB = 314 GB at cfg2).  counts[] is zeroed by the launcher.
+#define PC_CHUNK 4096
 __global__ void __launch_bounds__(256)
 k_dd_pair_count4(const double* __restrict__ X, i64 N, const int* __restrict__ pi, const int* __restrict__ pj,
-                 double a, double b, double c, double rmax2, i64* __restrict__ counts, int* __restrict__ frame_hit) {
+                 double a, double b, double c, double rmax2, unsigned long long* __restrict__ counts,
+                 int* __restrict__ frame_hit) {
     __shared__ double sh[8];
     const i64 p = blockIdx.x;
     const double* xi = X + (i64)pi[p] * 3 * N;
     const double* xj = X + (i64)pj[p] * 3 * N;
     const double L[3] = {a, b, c};
+    const i64 n_begin = (i64)blockIdx.y * PC_CHUNK;
+    const i64 n_end = n_begin + PC_CHUNK < N ? n_begin + PC_CHUNK : N;
     double cnt = 0.0;
-    for (i64 n = (i64)threadIdx.x * 4; n < N; n += 1024) {
+    for (i64 n = n_begin + (i64)threadIdx.x * 4; n < n_end; n += 1024) {
         double ci[3][4], cj[3][4];
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
@@ -276,15 +283,20 @@ k_dd_pair_count4(const double* __restrict__ X, i64 N, const int* __restrict__ pi
         }
     }
     const double t = block_sum_256(cnt, sh);
-    if (threadIdx.x == 0) counts[p] = (i64)t;
+    if (threadIdx.x == 0 && t > 0.0) atomicAdd(counts + p, (unsigned long long)t);
 }
 cudaError_t launch_dd_pair_count(const double* X, i64 N, const int* pi, const int* pj, i64 n_pairs, double a,
                                  double b, double c, double rmax, i64* counts, int* frame_hit, cudaStream_t st) {
     if (n_pairs <= 0) return cudaSuccess;
-    if ((N & 3) == 0 && ((uintptr_t)X & 31) == 0)
-        k_dd_pair_count4<<<(unsigned)n_pairs, 256, 0, st>>>(X, N, pi, pj, a, b, c, rmax * rmax, counts, frame_hit);
-    else
+    const i64 chunks = (N + PC_CHUNK - 1) / PC_CHUNK;
+    if ((N & 3) == 0 && ((uintptr_t)X & 31) == 0 && chunks <= 65535) {
+        cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(i64) * n_pairs, st);
+        if (e != cudaSuccess) return e;
+        k_dd_pair_count4<<<dim3((unsigned)n_pairs, (unsigned)chunks), 256, 0, st>>>(
+            X, N, pi, pj, a, b, c, rmax * rmax, reinterpret_cast<unsigned long long*>(counts), frame_hit);
+    } else {
         k_dd_pair_count<<<(unsigned)n_pairs, 256, 0, st>>>(X, N, pi, pj, a, b, c, rmax * rmax, counts, frame_hit);
+    }
     return cudaGetLastError();
 }
 

@@ -153,7 +153,7 @@ def test_dd_kernels_vs_oracle_bigger(ops):
             assert info["partial"] > 0 and info["full"] > 0
 
 
-@pytest.mark.parametrize("F", [64, 62, 1028])   # 32-byte loads (F % 4 == 0, more than one sweep of 1024 frames) and the scalar form
+@pytest.mark.parametrize("F", [64, 62, 8200])   # 32-byte loads (F % 4 == 0; 8200: three frame chunks, atomic counts) and the scalar form
 def test_dd_pair_count_bit_exact_presence(ops, F):
     """Presence (r2 < rmax^2) must agree with pdist_ortho's decision for every pair-frame."""
     from dynpy_b200 import synth
