@@ -43,6 +43,9 @@ struct GeomParams {
     int pair_fastest;  // 1: grid = (pair slots, frame chunks) — all pairs of the batch sweep one chunk of frames before the
                        // next, so the coordinates of that chunk (A x 3 x 2048 frames) are read from DRAM once per batch
                        // and then from L2; 0: grid = (frame chunks, pair slots), every pair streams its atoms from DRAM
+                       // (ncu at cfg2, 1640 pairs per launch: DRAM reads 3.88 -> 1.53 GB, DRAM busy 80 -> 61 %, time 1.36 ->
+                       // 1.34 ms: with the reads gone the kernel is bound by load latency at 16 warps per SM, its 2 x 4
+                       // frames per thread need the 128 registers — 80 or 64 registers spill 250 - 400 B)
 };
 
 // grid: (frame chunks of 1024, pair slots); 256 threads x 4 frames
