@@ -15,6 +15,10 @@
 //   step 3  fft16 -> |X|^2 += into 16 registers; X index = t/16 + 16 (t%16) + 256 j.
 // The next row is pulled into L2 by one bulk prefetch while the current row is transformed.
 // fp64 instructions per point: 3*148/16 (codelets) + 4*15/16 + 4 + 4*15/16 + 2 = 41.3.
+//
+// The same row transform also serves the write epilogues of the generic engine (template parameter MODE): per-series
+// power spectra (staged through a second shared-memory region, stored as 256-byte runs) and the real outputs of the
+// inverse transforms (k = k1 + M1 k2, rows dealt round-robin over the CTAs).
 #pragma once
 #include "codelets.cuh"
 #include "fft_engine.cuh"
@@ -259,8 +263,8 @@ __global__ void __launch_bounds__(256, 2) k_rows2(const Rows2Params p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) dst[tid + 256 * i] = sr[tid + (tid >> 4) + 272 * i];
         } else {
-            // natural index k = k1 + M1 k2 (the M1 rows of a transform are consecutive units of the same CTA: the 32-byte
-            // sectors they share are completed in L2 a few microseconds apart)
+            // natural index k = k1 + M1 k2: consecutive k1 (consecutive CTAs of the grid, see RR above) fill the same
+            // 32-byte sectors at about the same time
             const i64 f = p.f_base + item;
             const bool two = MODE == ROWS2_WRITE_REAL2 && 2 * f + 1 < p.n_series;
             double* o0 = p.out + (MODE == ROWS2_WRITE_REAL2 ? 2 * f : f) * p.n_out;
