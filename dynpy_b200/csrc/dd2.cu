@@ -161,9 +161,56 @@ cudaError_t launch_rows2_write(Rows2Params p, int mode, int n_sm, cudaStream_t s
         case ROWS2_WRITE_REAL: ROWS2_WRITE_CASE(ROWS2_WRITE_REAL); break;
         case ROWS2_WRITE_POWER: ROWS2_WRITE_CASE(ROWS2_WRITE_POWER); break;
         case ROWS2_WRITE_REAL2: ROWS2_WRITE_CASE(ROWS2_WRITE_REAL2); break;
+        case ROWS2_WRITE_INPLACE: ROWS2_WRITE_CASE(ROWS2_WRITE_INPLACE); break;
         default: return cudaErrorInvalidValue;
     }
 #undef ROWS2_WRITE_CASE
+    return cudaGetLastError();
+}
+
+// T[f][k1][k2] (complex rows written back by k_rows2<.., ROWS2_WRITE_INPLACE>) -> real outputs in natural order
+// k = k1 + M1 k2 < n_out:  planes = 1: out[f_base + f][k] = scale Re;  planes = 2: out[2 (f_base + f)][k] = scale Re,
+// out[2 (f_base + f) + 1][k] = scale Im (while that row exists).  Tiled transpose: reads are 512-byte runs along k2,
+// writes 256-byte runs along k1.
+__global__ void __launch_bounds__(256) k_rows_to_natural(const cd* __restrict__ T, double* __restrict__ out, int M1, int rs,
+                                                         i64 f_base, i64 n_out, i64 n_series, int planes, double scale) {
+    __shared__ cd tile[32][33];
+    const i64 f = blockIdx.z;
+    const cd* in = T + f * (i64)M1 * rs;
+    const int k2_0 = blockIdx.x * 32, k1_0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + j;
+        if (k1 < M1) tile[j][tx] = in[(i64)k1 * rs + k2_0 + tx];
+    }
+    __syncthreads();
+    const i64 fo = f_base + f;
+    double* o0 = out + (planes == 2 ? 2 * fo : fo) * n_out;
+    const bool two = planes == 2 && 2 * fo + 1 < n_series;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int k1 = k1_0 + tx;
+        const i64 k = (i64)k1 + (i64)M1 * (k2_0 + j);
+        if (k1 < M1 && k < n_out) {
+            const cd v = tile[tx][j];
+            o0[k] = v.x * scale;
+            if (two) o0[n_out + k] = v.y * scale;
+        }
+    }
+}
+cudaError_t launch_rows_to_natural(const cd* T, double* out, int M1, int rs, i64 n_fft, i64 f_base, i64 n_out, i64 n_series,
+                                   int planes, double scale, cudaStream_t st) {
+    if (n_fft <= 0 || n_out <= 0) return cudaSuccess;
+    const i64 k2_end = (n_out + M1 - 1) / M1;   // k2 values that hold any k < n_out
+    const unsigned gx = (unsigned)((k2_end + 31) / 32 < 128 ? (k2_end + 31) / 32 : 128);
+    ProfScope prof(PROF_ROWS, st);
+    for (i64 f0 = 0; f0 < n_fft; f0 += 32768) {
+        const i64 cnt = n_fft - f0 < 32768 ? n_fft - f0 : 32768;
+        dim3 grid(gx, (unsigned)((M1 + 31) / 32), (unsigned)cnt);
+        k_rows_to_natural<<<grid, 256, 0, st>>>(T + f0 * (i64)M1 * rs, out, M1, rs, f_base + f0, n_out, n_series, planes,
+                                                scale);
+    }
     return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@ namespace dynpy {
 // defined in dd2.cu
 cudaError_t launch_rows2(Rows2Params p, const int* sel, int nsel, bool fix, int n_sm, cudaStream_t st);
 cudaError_t launch_rows2_write(Rows2Params p, int mode, int n_sm, cudaStream_t st);
+cudaError_t launch_rows_to_natural(const cd* T, double* out, int M1, int rs, i64 n_fft, i64 f_base, i64 n_out, i64 n_series,
+                                   int planes, double scale, cudaStream_t st);
 
 template <int L, bool TWO_PASS, class Loader, int MODE>
 static cudaError_t launch_rows_L(const Loader& ld, const EpiParams& ep, const cd* tw, i64 f0, i64 f1, int gy,
@@ -145,16 +147,25 @@ static cudaError_t run_forward(const Loader& ld, const EpiParams& ep, i64 n_fft,
             for (int s = 0; s < nslots; ++s) sel[s] = s;
             e = launch_rows2(rp, sel, nslots, false, n_sm, st);
         } else {
-            // write epilogues (per-series power spectra, inverse transforms): the same row kernel; for A/B,
-            // DYNPY_ROWS_GENERIC=1 keeps the plain radix kernel k_rows for all of them, =2 for the real-output modes only
+            // write epilogues (per-series power spectra, inverse transforms): the same row kernel.  Real outputs
+            // (inverse transforms) are written back into T row by row and transposed to natural order by a second
+            // kernel.  For A/B, DYNPY_ROWS_GENERIC=1 keeps the plain radix kernel k_rows for all epilogues, =2 for the
+            // real-output modes only, =3 uses the row kernel's scattered 8-byte stores for them
             static int generic = -1;
             if (generic < 0) { const char* g = getenv("DYNPY_ROWS_GENERIC"); generic = g ? atoi(g) : 0; }
-            if (generic == 0 || (generic == 2 && MODE == EPI_WRITE_POWER)) {
+            if (generic == 0 || generic == 3 || (generic == 2 && MODE == EPI_WRITE_POWER)) {
                 Rows2Params rp;
                 memset(&rp, 0, sizeof(rp));
                 rp.T = T; rp.M = M; rp.M1 = M1; rp.rs = DYNPY_ROW_LEN; rp.items = nb; rp.twp = tw;
                 rp.out = ep.out; rp.f_base = f0; rp.n_out = ep.n_out; rp.n_series = ep.n_series; rp.scale = ep.scale;
-                e = launch_rows2_write(rp, MODE, n_sm, st);
+                if (MODE != EPI_WRITE_POWER && generic == 0) {
+                    e = launch_rows2_write(rp, ROWS2_WRITE_INPLACE, n_sm, st);
+                    if (e == cudaSuccess)
+                        e = launch_rows_to_natural(T, ep.out, M1, DYNPY_ROW_LEN, nb, f0, ep.n_out, ep.n_series,
+                                                   MODE == EPI_WRITE_REAL2 ? 2 : 1, ep.scale, st);
+                } else {
+                    e = launch_rows2_write(rp, MODE, n_sm, st);
+                }
             } else {
                 TLoader tl;
                 tl.T = T; tl.M1 = M1; tl.f_base = f0;
